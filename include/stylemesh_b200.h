@@ -1,0 +1,143 @@
+/* stylemesh_b200 — C-ABI of the B200-native StyleMesh texture-optimisation hot path.
+ *
+ * The reference (lukasHoel/stylemesh) has NO native/FFI boundary: every FLOP of its hot path runs inside
+ * third-party torch ops called from Python.  This header is therefore the boundary a maintainer would bind
+ * (ctypes / cffi / a torch custom-op shim) underneath the reference's Python modules; each entry point names the
+ * reference call site(s) it replaces.  Conventions:
+ *   - plain C types only; every tensor is a raw DEVICE pointer plus explicit sizes (host pointers are marked);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is asynchronous on it;
+ *   - return value: 0 = ok, negative = error (message via smb_last_error(), thread-local);
+ *   - the library never touches the reference's CPU path and has no CPU fallback.
+ *
+ * Storage formats
+ *   image / texture / gradients : fp32 planar (C,H,W), exactly the reference tensors.
+ *   UV grid                     : fp32 (H,W,2) in [-1,1]  (model/texture/utils.py:56-60 to_grid()).
+ *   VGG activations (internal)  : channels-last bf16 hi/lo planes, x = hi + lo (fp32-grade);
+ *                                 exported to fp32 NCHW on request.
+ */
+#ifndef STYLEMESH_B200_H
+#define STYLEMESH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB_ABI_VERSION 1
+#define SMB_NUM_VGG_CONVS 13 /* conv1_1 .. conv5_1: the layers the style/content loss can read */
+
+/* implementation selectors for smb_ctx_set_impl */
+#define SMB_IMPL_SIMT 0 /* fp32 CUDA-core cross-check kernels            */
+#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (default product) */
+
+typedef struct smb_ctx smb_ctx;
+
+int smb_abi_version(void);
+const char* smb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Texture side
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Replaces NeuralTexture.forward / HierarchicalNeuralTexture.forward
+ * (model/texture/texture.py:41-54, 96-100): out[c][y][x] = sum_l bilinear(clamp(layer_l), grid), border padding,
+ * align_corners=True.  The clamp is applied on read; the stored texture is clamped by smb_adam_step.
+ * layers: HOST array of num_layers device pointers, layer l is (channels, layer_h[l], layer_w[l]) fp32. */
+int smb_uv_sample_fwd(const float* const* layers, const int* layer_w, const int* layer_h, int num_layers,
+                      int channels, const float* grid, int H, int W, float clamp_lo, float clamp_hi, float* out,
+                      void* stream);
+
+/* Debug/parity export of the exact UV index arithmetic (ATen GridSampler.h:27-36,58-60,143-171):
+ * xy0[p] = (x0,y0) north-west texel, w4[p] = (nw,ne,sw,se) weights, for a (tex_h, tex_w) layer. */
+int smb_uv_texel_index(const float* grid, int num_pixels, int tex_w, int tex_h, int* xy0, float* w4, void* stream);
+
+/* Replaces grid_sampler_2d_backward (input gradient only) for all layers plus the two gradient hooks of
+ * model/model.py:198-202 (angle) and :247-251 (depth interpolation weight):
+ *   grad_layers[l][c][y][x] += w_corner * grad_out[c][p] * hook0[p] * hook1[p]      (hook pointers may be NULL)
+ * Accumulates (the caller / smb_adam_step keeps the buffers zeroed). */
+int smb_uv_scatter_bwd(float* const* grad_layers, const int* layer_w, const int* layer_h, int num_layers,
+                       int channels, const float* grid, int H, int W, const float* grad_out, const float* hook0,
+                       const float* hook1, void* stream);
+
+/* Replaces torch.optim.Adam.step (model/model.py:395) fused with NeuralTexture.normalize() (texture.py:41-44) and
+ * the gradient of HierarchicalNeuralTexture.regularizer (texture.py:102-108):
+ *   x = clamp(p); g' = grad*grad_scale + reg_coef*x; Adam(m, v, g'); p = x - lr/bc1 * m/(sqrt(v)/sqrt(bc2)+eps);
+ *   grad = 0.   step is 1-based.  reg_coef = lambda_reg * w_l * 2 / numel(layer). */
+int smb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float clamp_lo, float clamp_hi, float reg_coef,
+                  float grad_scale, void* stream);
+
+/* Value of one regulariser term: *out_accum += coef * sum(clamp(param)^2)   (coef = lambda_reg*w_l/numel). */
+int smb_texreg_value(const float* param, int64_t n, float coef, float clamp_lo, float clamp_hi, float* out_accum,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
+ * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the
+ * autograd backward of all of them).
+ * ------------------------------------------------------------------------------------------------------- */
+smb_ctx* smb_ctx_create(void);
+void smb_ctx_destroy(smb_ctx* ctx);
+
+/* conv_impl / gram_impl: SMB_IMPL_SIMT or SMB_IMPL_TC. */
+int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl);
+
+/* weights_oihw[i]: HOST fp32 (Cout,Cin,3,3) of conv i in state_dict order conv1_1..conv5_1; bias[i]: HOST (Cout). */
+int smb_ctx_load_vgg(smb_ctx* ctx, const float* const* weights_oihw, const float* const* bias, int num_convs);
+
+/* Select (and lazily allocate) the working set for an H x W input; returns a slot id >= 0.  Several slots can be
+ * alive at once (one per pyramid level / view resolution); a slot keeps its forward activations until reused. */
+int smb_level_begin(smb_ctx* ctx, int H, int W);
+
+/* VGG forward of image (3,H,W) fp32 up to and including conv `last_conv` (0 = conv1_1 .. 12 = conv5_1). */
+int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv, void* stream);
+
+/* Export relu(conv_i) as fp32 (C,h,w); query its shape. */
+int smb_level_feature_shape(smb_ctx* ctx, int slot, int conv, int* C, int* h, int* w);
+int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, void* stream);
+
+/* Masked Gram of relu(conv_i):  G = inv_n * sum_p m_p F_p F_p^T  -> gram_out (C x C fp32). rowmask may be NULL. */
+int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, float* gram_out,
+                   void* stream);
+
+/* One style term on relu(conv_i): masked Gram, (optional running average), weighted MSE against up to two
+ * C x C targets, and the gradient w.r.t. the features accumulated into the slot's pending gradient of that layer.
+ *   loss_accum[0] += coef0 * mean((Y0 - Ghat)^2) + coef1 * mean((Y1 - Ghat)^2)
+ * prev_sum/avg_len implement gram_mode 'average' (cs:319-323): Ghat = (G + prev_sum)/avg_len; pass NULL/1. */
+int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, const float* target0,
+                         float coef0, const float* target1, float coef1, const float* prev_sum, float avg_len,
+                         float* gram_out, float* loss_accum, void* stream);
+
+/* Content term on relu(conv_i): loss_accum[0] += coef_loss * sum_p m_p |F_p - T_p|^2 and the gradient
+ * coef_grad * m_p * (F_p - T_p) accumulated into the pending gradient.  target: fp32 channels-last (h*w, C). */
+int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target_nhwc, const float* rowmask,
+                           float coef_loss, float coef_grad, float* loss_accum, void* stream);
+
+/* Back-propagate every pending term of the slot to the input image: d_image (3,H,W) fp32 is overwritten.
+ * Clears the pending gradients. */
+int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream);
+
+/* Bytes of device memory currently owned by the context. */
+int64_t smb_ctx_device_bytes(smb_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Unit-level entry points (used by the parity tests to localise a failure to one kernel).
+ * tensors are fp32 NCHW on the device; conversion to the internal planes happens inside.
+ * ------------------------------------------------------------------------------------------------------- */
+/* y = [relu](conv3x3(x, w, b)), x (Cin,H,W), w HOST (Cout,Cin,3,3), b HOST (Cout) or NULL, y (Cout,H,W).
+ * transpose_flip != 0 computes the data gradient instead: x is dY (Cout,H,W), y is dX (Cin,H,W), no bias. */
+int smb_unit_conv3x3(int impl, const float* x, int Cin, int H, int W, const float* w_host, const float* b_host,
+                     int Cout, int relu, int transpose_flip, float* y, void* stream);
+/* y (C,H/2,W/2) = maxpool2x2(x (C,H,W)) */
+int smb_unit_maxpool(const float* x, int C, int H, int W, float* y, void* stream);
+/* dx (C,H,W) = maxpool/relu backward of g (C,H/2,W/2) through y (C,H,W) */
+int smb_unit_maxpool_bwd(const float* g, const float* y, int C, int H, int W, float* dx, void* stream);
+/* G (C,C) = inv_n * sum_p m_p F_p F_p^T for F (C,H,W) */
+int smb_unit_gram(int impl, const float* f, int C, int H, int W, const float* rowmask, float inv_n, float* G,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STYLEMESH_B200_H */

@@ -1,0 +1,100 @@
+"""Build the sm_100a shared library (C-ABI, include/stylemesh_b200.h) in-tree with nvcc.
+
+    python -m stylemesh_b200.build [--force]
+
+The library is written to stylemesh_b200/lib/libstylemesh_b200.so (git-ignored, shipped to the GPU box by gpurun).
+nvcc cross-compiles for sm_100a without a GPU, so this also is the "does it build" check of __graft_entry__.build().
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libstylemesh_b200.so")
+STAMP_PATH = os.path.join(LIB_DIR, "build.stamp")
+
+SOURCES = ["texture_kernels.cu", "vgg_simt_kernels.cu", "tc_kernels.cu", "engine.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _source_hash() -> str:
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join("..", "..", "include", "stylemesh_b200.h"))
+    for f in files:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
+        return False
+    with open(STAMP_PATH) as fh:
+        return fh.read().strip() == _source_hash()
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    """Compile (if the sources changed) and return the library path."""
+    if not force and is_current():
+        return LIB_PATH
+    nvcc = _nvcc()
+    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print("[stylemesh_b200.build]", " ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    if verbose:
+        print("[stylemesh_b200.build]", " ".join(link), flush=True)
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(STAMP_PATH, "w") as fh:
+        fh.write(_source_hash())
+    return LIB_PATH
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument("--force", action="store_true")
+    args = ap.parse_args(argv)
+    print(build(force=args.force))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,693 @@
+// Host-side engine behind the C-ABI (include/stylemesh_b200.h): VGG weights in kernel layout, per-resolution
+// working sets ("slots"), forward / loss-term / backward orchestration.  Every arithmetic step is one of the
+// kernels in texture_kernels.cu, vgg_simt_kernels.cu or tc_kernels.cu; nothing here computes on the CPU except
+// the one-time weight repacking.
+#include <cstdarg>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/stylemesh_b200.h"
+#include "smb_common.cuh"
+#include "smb_kernels.h"
+
+namespace smb {
+
+// ---- error string ------------------------------------------------------------------------------------------
+static thread_local char g_err[2048] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- VGG-19 topology up to conv5_1 (model/losses/content_and_style_losses.py:11-32,47-66) ---------------------
+static const int kCin[SMB_NUM_VGG_CONVS] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512};
+static const int kCout[SMB_NUM_VGG_CONVS] = {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512};
+static const bool kPoolBefore[SMB_NUM_VGG_CONVS] = {false, false, true, false, true, false, false,
+                                                    false, true,  false, false, false, true};
+
+struct DeviceArena {
+  std::vector<void*> ptrs;
+  int64_t bytes = 0;
+  template <typename T>
+  int alloc(T** out, int64_t count) {
+    void* p = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+      return SMB_ERR_CUDA;
+    }
+    ptrs.push_back(p);
+    bytes += (int64_t)n;
+    *out = reinterpret_cast<T*>(p);
+    return SMB_OK;
+  }
+  int alloc_act(Act* a, int H, int W, int C) {
+    a->H = H;
+    a->W = W;
+    a->C = C;
+    int rc = alloc(&a->hi, a->elems());
+    if (rc) return rc;
+    return alloc(&a->lo, a->elems());
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+  }
+  ~DeviceArena() { release(); }
+};
+
+struct ConvLayer {
+  PackedB fwd, dgrad;
+  float* bias = nullptr;
+  float* w_oihw = nullptr;   // device copy of the original layout (first layer only)
+};
+
+struct Slot {
+  int H = 0, W = 0;
+  int h[SMB_NUM_VGG_CONVS], w[SMB_NUM_VGG_CONVS];
+  Act y[SMB_NUM_VGG_CONVS];        // relu(conv_i)
+  Act pooled[SMB_NUM_VGG_CONVS];   // input of conv_i when a pool precedes it
+  Act dz[SMB_NUM_VGG_CONVS];       // gradient w.r.t. the pre-activation of conv_i (lazy)
+  float* pend[SMB_NUM_VGG_CONVS];  // pending loss gradient w.r.t. relu(conv_i), fp32 [P][C] (lazy)
+  bool has_pend[SMB_NUM_VGG_CONVS];
+  float* gpool[SMB_NUM_VGG_CONVS]; // fp32 gradient w.r.t. pooled input of conv_i (lazy)
+  Act fm;                          // masked copy scratch (sized for the largest layer, lazy)
+  float* gram_partial = nullptr;
+  int64_t gram_partial_elems = 0;
+  __nv_bfloat16 *bmat_hi = nullptr, *bmat_lo = nullptr;
+  int last_done = -1;
+  DeviceArena arena;
+  Slot() {
+    for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) {
+      pend[i] = nullptr;
+      has_pend[i] = false;
+      gpool[i] = nullptr;
+    }
+  }
+};
+
+}  // namespace smb
+
+using namespace smb;
+
+struct smb_ctx {
+  int conv_impl = IMPL_TC, gram_impl = IMPL_TC;
+  bool vgg_loaded = false;
+  ConvLayer conv[SMB_NUM_VGG_CONVS];
+  DeviceArena weights;
+  std::vector<std::unique_ptr<Slot>> slots;
+};
+
+namespace smb {
+
+static int upload_packed(DeviceArena& ar, PackedB* out, const std::vector<float>& vals, int taps, int N, int K) {
+  const int64_t n = (int64_t)taps * N * K;
+  std::vector<uint16_t> hi(n), lo(n);
+  for (int64_t i = 0; i < n; ++i) {
+    const uint16_t h = host_f2bf(vals[i]);
+    hi[i] = h;
+    lo[i] = host_f2bf(vals[i] - host_bf2f(h));
+  }
+  out->taps = taps;
+  out->N = N;
+  out->K = K;
+  int rc = ar.alloc(&out->hi, n);
+  if (rc) return rc;
+  rc = ar.alloc(&out->lo, n);
+  if (rc) return rc;
+  SMB_CUDA_CHECK(cudaMemcpy(out->hi, hi.data(), n * 2, cudaMemcpyHostToDevice));
+  SMB_CUDA_CHECK(cudaMemcpy(out->lo, lo.data(), n * 2, cudaMemcpyHostToDevice));
+  return SMB_OK;
+}
+
+// forward operand: B[tap=r*3+s][n=co][k=ci] = w[co][ci][r][s]
+static void pack_fwd(const float* w, int Cout, int Cin, std::vector<float>& out) {
+  out.resize((size_t)9 * Cout * Cin);
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s)
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+          out[((size_t)(r * 3 + s) * Cout + co) * Cin + ci] = w[(((size_t)co * Cin + ci) * 3 + r) * 3 + s];
+}
+// data-gradient operand: B[tap=r*3+s][n=ci][k=co] = w[co][ci][2-r][2-s]
+static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& out) {
+  out.resize((size_t)9 * Cout * Cin);
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+          out[((size_t)(r * 3 + s) * Cin + ci) * Cout + co] = w[(((size_t)co * Cin + ci) * 3 + (2 - r)) * 3 + (2 - s)];
+}
+
+static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  return impl == IMPL_TC ? launch_igemm_tc(a, b, ep, st) : launch_igemm_simt(a, b, ep, st);
+}
+static int gram(int impl, const Act& fm, float* partial, int nsplit, cudaStream_t st) {
+  return impl == IMPL_TC ? launch_gram_tc(fm, partial, nsplit, st) : launch_gram_simt(fm, partial, nsplit, st);
+}
+
+static Slot* get_slot(smb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) {
+    set_error("invalid context or slot id %d", slot);
+    return nullptr;
+  }
+  return ctx->slots[slot].get();
+}
+
+static int ensure_scratch(Slot& s, int conv_impl_unused) {
+  (void)conv_impl_unused;
+  if (!s.fm.hi) {
+    int64_t max_elems = 0;
+    for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) max_elems = std::max(max_elems, s.y[i].elems());
+    s.fm.H = 1;
+    s.fm.W = 1;
+    s.fm.C = 1;
+    int rc = s.arena.alloc(&s.fm.hi, max_elems);
+    if (rc) return rc;
+    rc = s.arena.alloc(&s.fm.lo, max_elems);
+    if (rc) return rc;
+  }
+  if (!s.bmat_hi) {
+    int rc = s.arena.alloc(&s.bmat_hi, 512 * 512);
+    if (rc) return rc;
+    rc = s.arena.alloc(&s.bmat_lo, 512 * 512);
+    if (rc) return rc;
+  }
+  return SMB_OK;
+}
+
+static int ensure_gram_partial(Slot& s, int64_t elems) {
+  if (s.gram_partial_elems >= elems) return SMB_OK;
+  s.gram_partial_elems = elems;
+  return s.arena.alloc(&s.gram_partial, elems);   // the previous (smaller) block stays in the arena until destroy
+}
+
+// masked Gram partials of layer `conv`; returns the operand actually used (masked copy or the features)
+static int gram_partials(smb_ctx* ctx, Slot& s, int conv, const float* rowmask, Act* used, int* nsplit,
+                         cudaStream_t st) {
+  int rc = ensure_scratch(s, ctx->conv_impl);
+  if (rc) return rc;
+  Act src = s.y[conv];
+  if (rowmask) {
+    Act fm = s.fm;
+    fm.H = src.H;
+    fm.W = src.W;
+    fm.C = src.C;
+    rc = launch_mask_rows(src, rowmask, fm, st);
+    if (rc) return rc;
+    src = fm;
+  }
+  const int ns = gram_num_splits(src.pixels(), src.C, ctx->gram_impl);
+  rc = ensure_gram_partial(s, (int64_t)ns * src.C * src.C);
+  if (rc) return rc;
+  rc = gram(ctx->gram_impl, src, s.gram_partial, ns, st);
+  if (rc) return rc;
+  *used = src;
+  *nsplit = ns;
+  return SMB_OK;
+}
+
+__global__ void gram_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t CC, float inv_n,
+                                   float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < CC; e += stride) {
+    float g = 0.f;
+    for (int s = 0; s < nsplit; ++s) g += partial[(int64_t)s * CC + e];
+    out[e] = g * inv_n;
+  }
+}
+
+}  // namespace smb
+
+// =============================================================================================================
+// C-ABI
+// =============================================================================================================
+extern "C" {
+
+int smb_abi_version(void) { return SMB_ABI_VERSION; }
+const char* smb_last_error(void) { return smb::get_error(); }
+
+// ---- texture ------------------------------------------------------------------------------------------------
+static int fill_layers(TexLayerSet* t, float* const* layers, const int* lw, const int* lh, int L, int C) {
+  SMB_REQUIRE(L >= 1 && L <= SMB_MAX_TEX_LAYERS, "num_layers=%d out of range [1,%d]", L, SMB_MAX_TEX_LAYERS);
+  SMB_REQUIRE(C >= 1 && C <= SMB_MAX_TEX_CHANNELS, "channels=%d out of range [1,%d]", C, SMB_MAX_TEX_CHANNELS);
+  t->L = L;
+  t->C = C;
+  for (int l = 0; l < L; ++l) {
+    SMB_REQUIRE(layers[l] != nullptr && lw[l] >= 1 && lh[l] >= 1, "texture layer %d is null or empty", l);
+    t->ptr[l] = layers[l];
+    t->W[l] = lw[l];
+    t->H[l] = lh[l];
+  }
+  return SMB_OK;
+}
+
+int smb_uv_sample_fwd(const float* const* layers, const int* layer_w, const int* layer_h, int num_layers,
+                      int channels, const float* grid, int H, int W, float clamp_lo, float clamp_hi, float* out,
+                      void* stream) {
+  SMB_REQUIRE(layers && layer_w && layer_h && grid && out, "uv_sample_fwd: null argument");
+  SMB_REQUIRE(H >= 0 && W >= 0, "uv_sample_fwd: negative size");
+  TexLayerSet t;
+  int rc = fill_layers(&t, const_cast<float* const*>(layers), layer_w, layer_h, num_layers, channels);
+  if (rc) return rc;
+  return launch_uv_sample_fwd(t, grid, H, W, clamp_lo, clamp_hi, out, (cudaStream_t)stream);
+}
+
+int smb_uv_texel_index(const float* grid, int num_pixels, int tex_w, int tex_h, int* xy0, float* w4, void* stream) {
+  SMB_REQUIRE(grid && xy0 && w4 && tex_w >= 1 && tex_h >= 1 && num_pixels >= 0, "uv_texel_index: bad argument");
+  return launch_uv_texel_index(grid, num_pixels, tex_w, tex_h, xy0, w4, (cudaStream_t)stream);
+}
+
+int smb_uv_scatter_bwd(float* const* grad_layers, const int* layer_w, const int* layer_h, int num_layers,
+                       int channels, const float* grid, int H, int W, const float* grad_out, const float* hook0,
+                       const float* hook1, void* stream) {
+  SMB_REQUIRE(grad_layers && layer_w && layer_h && grid && grad_out, "uv_scatter_bwd: null argument");
+  TexLayerSet t;
+  int rc = fill_layers(&t, grad_layers, layer_w, layer_h, num_layers, channels);
+  if (rc) return rc;
+  return launch_uv_scatter_bwd(t, grid, H, W, grad_out, hook0, hook1, (cudaStream_t)stream);
+}
+
+int smb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float clamp_lo, float clamp_hi, float reg_coef,
+                  float grad_scale, void* stream) {
+  SMB_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0, "adam_step: null argument");
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, clamp_lo, clamp_hi, reg_coef,
+                     grad_scale, (cudaStream_t)stream);
+}
+
+int smb_texreg_value(const float* param, int64_t n, float coef, float clamp_lo, float clamp_hi, float* out_accum,
+                     void* stream) {
+  SMB_REQUIRE(param && out_accum && n >= 0, "texreg_value: null argument");
+  return launch_sumsq_clamped(param, n, coef, clamp_lo, clamp_hi, out_accum, (cudaStream_t)stream);
+}
+
+// ---- context --------------------------------------------------------------------------------------------------
+smb_ctx* smb_ctx_create(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("smb_ctx_create: no CUDA device is current (%s)", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    set_error("smb_ctx_create: device %d is not an sm_100-class GPU (compute capability %d.%d); this library "
+              "contains sm_100a code only", dev, prop.major, prop.minor);
+    return nullptr;
+  }
+  return new smb_ctx();
+}
+
+void smb_ctx_destroy(smb_ctx* ctx) { delete ctx; }
+
+int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl) {
+  SMB_REQUIRE(ctx, "null context");
+  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC) && (gram_impl == IMPL_SIMT || gram_impl == IMPL_TC),
+              "impl must be SMB_IMPL_SIMT or SMB_IMPL_TC");
+  ctx->conv_impl = conv_impl;
+  ctx->gram_impl = gram_impl;
+  return SMB_OK;
+}
+
+int smb_ctx_load_vgg(smb_ctx* ctx, const float* const* weights_oihw, const float* const* bias, int num_convs) {
+  SMB_REQUIRE(ctx && weights_oihw && bias, "load_vgg: null argument");
+  SMB_REQUIRE(num_convs == SMB_NUM_VGG_CONVS, "load_vgg: expected %d conv layers (conv1_1..conv5_1), got %d",
+              SMB_NUM_VGG_CONVS, num_convs);
+  ctx->weights.release();
+  ctx->vgg_loaded = false;
+  std::vector<float> tmp;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) {
+    SMB_REQUIRE(weights_oihw[i] && bias[i], "load_vgg: conv %d has a null weight or bias", i);
+    ConvLayer& c = ctx->conv[i];
+    int rc = ctx->weights.alloc(&c.bias, kCout[i]);
+    if (rc) return rc;
+    SMB_CUDA_CHECK(cudaMemcpy(c.bias, bias[i], kCout[i] * sizeof(float), cudaMemcpyHostToDevice));
+    if (i == 0) {
+      const int64_t n = (int64_t)kCout[0] * kCin[0] * 9;
+      rc = ctx->weights.alloc(&c.w_oihw, n);
+      if (rc) return rc;
+      SMB_CUDA_CHECK(cudaMemcpy(c.w_oihw, weights_oihw[0], n * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+      pack_fwd(weights_oihw[i], kCout[i], kCin[i], tmp);
+      rc = upload_packed(ctx->weights, &c.fwd, tmp, 9, kCout[i], kCin[i]);
+      if (rc) return rc;
+      pack_dgrad(weights_oihw[i], kCout[i], kCin[i], tmp);
+      rc = upload_packed(ctx->weights, &c.dgrad, tmp, 9, kCin[i], kCout[i]);
+      if (rc) return rc;
+    }
+  }
+  ctx->vgg_loaded = true;
+  return SMB_OK;
+}
+
+int smb_level_begin(smb_ctx* ctx, int H, int W) {
+  if (!ctx) {
+    set_error("null context");
+    return SMB_ERR_ARG;
+  }
+  SMB_REQUIRE(H >= 16 && W >= 16, "level_begin: input %dx%d is too small for four 2x2 pools", H, W);
+  for (size_t i = 0; i < ctx->slots.size(); ++i)
+    if (ctx->slots[i]->H == H && ctx->slots[i]->W == W) return (int)i;
+  std::unique_ptr<Slot> s(new Slot());
+  s->H = H;
+  s->W = W;
+  int h = H, w = W;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) {
+    if (kPoolBefore[i]) {
+      h /= 2;
+      w /= 2;
+      int rc = s->arena.alloc_act(&s->pooled[i], h, w, kCin[i]);
+      if (rc) return rc;
+    }
+    s->h[i] = h;
+    s->w[i] = w;
+    int rc = s->arena.alloc_act(&s->y[i], h, w, kCout[i]);
+    if (rc) return rc;
+  }
+  ctx->slots.push_back(std::move(s));
+  return (int)ctx->slots.size() - 1;
+}
+
+int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  Slot& s = *sp;
+  SMB_REQUIRE(ctx->vgg_loaded, "level_forward: VGG weights not loaded (smb_ctx_load_vgg)");
+  SMB_REQUIRE(image && last_conv >= 0 && last_conv < SMB_NUM_VGG_CONVS, "level_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    Epilogue ep;
+    ep.relu = 1;
+    ep.out_hi = s.y[0].hi;
+    ep.out_lo = s.y[0].lo;
+    int rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
+    if (rc) return rc;
+  }
+  for (int i = 1; i <= last_conv; ++i) {
+    Act x = s.y[i - 1];
+    if (kPoolBefore[i]) {
+      int rc = launch_maxpool_fwd(s.y[i - 1], s.pooled[i], st);
+      if (rc) return rc;
+      x = s.pooled[i];
+    }
+    Epilogue ep;
+    ep.bias = ctx->conv[i].bias;
+    ep.relu = 1;
+    ep.out_hi = s.y[i].hi;
+    ep.out_lo = s.y[i].lo;
+    int rc = igemm(ctx->conv_impl, x, ctx->conv[i].fwd, ep, st);
+    if (rc) return rc;
+  }
+  s.last_done = last_conv;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;
+  return SMB_OK;
+}
+
+int smb_level_feature_shape(smb_ctx* ctx, int slot, int conv, int* C, int* h, int* w) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  SMB_REQUIRE(conv >= 0 && conv < SMB_NUM_VGG_CONVS && C && h && w, "feature_shape: bad argument");
+  *C = kCout[conv];
+  *h = sp->h[conv];
+  *w = sp->w[conv];
+  return SMB_OK;
+}
+
+int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && out_nchw, "get_feature: conv %d not computed (last=%d)", conv,
+              sp->last_done);
+  return launch_act_to_nchw(sp->y[conv], out_nchw, (cudaStream_t)stream);
+}
+
+int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, float* gram_out,
+                   void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && gram_out, "level_gram: conv %d not computed (last=%d)", conv,
+              sp->last_done);
+  cudaStream_t st = (cudaStream_t)stream;
+  Act used;
+  int ns = 0;
+  int rc = gram_partials(ctx, *sp, conv, rowmask, &used, &ns, st);
+  if (rc) return rc;
+  const int64_t CC = (int64_t)used.C * used.C;
+  gram_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st>>>(sp->gram_partial, ns, CC,
+                                                                                           inv_n, gram_out);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+static int ensure_pend(Slot& s, int conv) {
+  if (s.pend[conv]) return SMB_OK;
+  return s.arena.alloc(&s.pend[conv], s.y[conv].elems());
+}
+
+int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, const float* target0,
+                         float coef0, const float* target1, float coef1, const float* prev_sum, float avg_len,
+                         float* gram_out, float* loss_accum, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  Slot& s = *sp;
+  SMB_REQUIRE(conv >= 0 && conv <= s.last_done, "style_term: conv %d not computed (last=%d)", conv, s.last_done);
+  SMB_REQUIRE(target0 && loss_accum, "style_term: null target or loss accumulator");
+  cudaStream_t st = (cudaStream_t)stream;
+  Act used;
+  int ns = 0;
+  int rc = gram_partials(ctx, s, conv, rowmask, &used, &ns, st);
+  if (rc) return rc;
+  rc = launch_gram_mse(s.gram_partial, ns, used.C, inv_n, target0, coef0, target1, coef1, prev_sum,
+                       prev_sum ? avg_len : 1.f, gram_out, s.bmat_hi, s.bmat_lo, loss_accum, st);
+  if (rc) return rc;
+  if (inv_n == 0.f) return SMB_OK;   // empty mask: constant loss, zero gradient (cs:140-141)
+  rc = ensure_pend(s, conv);
+  if (rc) return rc;
+  // dF[p][c] (+)= sum_k Fm[p][k] * Bmat[c][k]
+  PackedB b;
+  b.hi = s.bmat_hi;
+  b.lo = s.bmat_lo;
+  b.taps = 1;
+  b.N = used.C;
+  b.K = used.C;
+  Epilogue ep;
+  ep.out_f32 = s.pend[conv];
+  if (s.has_pend[conv]) ep.addend = s.pend[conv];
+  rc = igemm(ctx->conv_impl, used, b, ep, st);
+  if (rc) return rc;
+  s.has_pend[conv] = true;
+  return SMB_OK;
+}
+
+int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target_nhwc, const float* rowmask,
+                           float coef_loss, float coef_grad, float* loss_accum, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  Slot& s = *sp;
+  SMB_REQUIRE(conv >= 0 && conv <= s.last_done, "content_term: conv %d not computed (last=%d)", conv, s.last_done);
+  SMB_REQUIRE(target_nhwc && rowmask && loss_accum, "content_term: null argument");
+  int rc = ensure_pend(s, conv);
+  if (rc) return rc;
+  if (!s.has_pend[conv])
+    SMB_CUDA_CHECK(cudaMemsetAsync(s.pend[conv], 0, s.y[conv].elems() * sizeof(float), (cudaStream_t)stream));
+  rc = launch_content_mse(s.y[conv], target_nhwc, rowmask, coef_loss, coef_grad, s.pend[conv], loss_accum,
+                          (cudaStream_t)stream);
+  if (rc) return rc;
+  s.has_pend[conv] = true;
+  return SMB_OK;
+}
+
+int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  Slot& s = *sp;
+  SMB_REQUIRE(d_image, "level_backward: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  int top = -1;
+  for (int i = s.last_done; i >= 0; --i)
+    if (s.has_pend[i]) {
+      top = i;
+      break;
+    }
+  if (top < 0) {   // no loss term touched this level: zero gradient
+    SMB_CUDA_CHECK(cudaMemsetAsync(d_image, 0, (size_t)3 * s.H * s.W * sizeof(float), st));
+    return SMB_OK;
+  }
+  for (int i = 0; i <= top; ++i)
+    if (!s.dz[i].hi) {
+      int rc = s.arena.alloc_act(&s.dz[i], s.h[i], s.w[i], kCout[i]);
+      if (rc) return rc;
+    }
+  // top of the chain: dz = pend ⊙ (y > 0)
+  int rc = launch_relu_mask_split(s.pend[top], s.y[top], s.dz[top], st);
+  if (rc) return rc;
+  for (int i = top; i >= 1; --i) {
+    const int j = i - 1;   // layer receiving the gradient
+    if (kPoolBefore[i]) {
+      if (!s.gpool[i]) {
+        rc = s.arena.alloc(&s.gpool[i], s.pooled[i].elems());
+        if (rc) return rc;
+      }
+      Epilogue ep;
+      ep.out_f32 = s.gpool[i];
+      rc = igemm(ctx->conv_impl, s.dz[i], ctx->conv[i].dgrad, ep, st);
+      if (rc) return rc;
+      rc = launch_maxpool_bwd_relu(s.gpool[i], s.has_pend[j] ? s.pend[j] : nullptr, s.y[j], s.dz[j], st);
+      if (rc) return rc;
+    } else {
+      Epilogue ep;
+      if (s.has_pend[j]) ep.addend = s.pend[j];
+      ep.sign_hi = s.y[j].hi;
+      ep.out_hi = s.dz[j].hi;
+      ep.out_lo = s.dz[j].lo;
+      rc = igemm(ctx->conv_impl, s.dz[i], ctx->conv[i].dgrad, ep, st);
+      if (rc) return rc;
+    }
+  }
+  rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
+  if (rc) return rc;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;
+  return SMB_OK;
+}
+
+int64_t smb_ctx_device_bytes(smb_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t b = ctx->weights.bytes;
+  for (auto& s : ctx->slots) b += s->arena.bytes;
+  return b;
+}
+
+// ---- unit-level entry points ------------------------------------------------------------------------------------
+int smb_unit_conv3x3(int impl, const float* x, int Cin, int H, int W, const float* w_host, const float* b_host,
+                     int Cout, int relu, int transpose_flip, float* y, void* stream) {
+  SMB_REQUIRE(x && w_host && y, "unit_conv3x3: null argument");
+  SMB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "unit_conv3x3: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceArena ar;
+  const int K = transpose_flip ? Cout : Cin, N = transpose_flip ? Cin : Cout;
+  Act a, o;
+  int rc = ar.alloc_act(&a, H, W, K);
+  if (rc) return rc;
+  rc = ar.alloc_act(&o, H, W, N);
+  if (rc) return rc;
+  std::vector<float> tmp;
+  PackedB b;
+  if (transpose_flip) pack_dgrad(w_host, Cout, Cin, tmp); else pack_fwd(w_host, Cout, Cin, tmp);
+  rc = upload_packed(ar, &b, tmp, 9, N, K);
+  if (rc) return rc;
+  float* bias = nullptr;
+  if (b_host && !transpose_flip) {
+    rc = ar.alloc(&bias, Cout);
+    if (rc) return rc;
+    SMB_CUDA_CHECK(cudaMemcpyAsync(bias, b_host, Cout * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  rc = launch_act_from_nchw(x, a, st);
+  if (rc) return rc;
+  Epilogue ep;
+  ep.bias = bias;
+  ep.relu = relu;
+  ep.out_hi = o.hi;
+  ep.out_lo = o.lo;
+  rc = igemm(impl, a, b, ep, st);
+  if (rc) return rc;
+  rc = launch_act_to_nchw(o, y, st);
+  if (rc) return rc;
+  SMB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SMB_OK;
+}
+
+int smb_unit_maxpool(const float* x, int C, int H, int W, float* y, void* stream) {
+  SMB_REQUIRE(x && y && C % 8 == 0, "unit_maxpool: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceArena ar;
+  Act a, o;
+  int rc = ar.alloc_act(&a, H, W, C);
+  if (rc) return rc;
+  rc = ar.alloc_act(&o, H / 2, W / 2, C);
+  if (rc) return rc;
+  rc = launch_act_from_nchw(x, a, st);
+  if (rc) return rc;
+  rc = launch_maxpool_fwd(a, o, st);
+  if (rc) return rc;
+  rc = launch_act_to_nchw(o, y, st);
+  if (rc) return rc;
+  SMB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SMB_OK;
+}
+
+namespace smb {
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * C) return;
+  const int64_t p = i / C;
+  const int c = (int)(i % C);
+  dst[i] = src[(int64_t)c * P + p];
+}
+}  // namespace smb
+
+int smb_unit_maxpool_bwd(const float* g, const float* y, int C, int H, int W, float* dx, void* stream) {
+  SMB_REQUIRE(g && y && dx && C % 8 == 0, "unit_maxpool_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceArena ar;
+  Act ya, dz;
+  int rc = ar.alloc_act(&ya, H, W, C);
+  if (rc) return rc;
+  rc = ar.alloc_act(&dz, H, W, C);
+  if (rc) return rc;
+  float* g_nhwc = nullptr;
+  const int64_t Pp = (int64_t)(H / 2) * (W / 2);
+  rc = ar.alloc(&g_nhwc, Pp * C);
+  if (rc) return rc;
+  rc = launch_act_from_nchw(y, ya, st);
+  if (rc) return rc;
+  if (Pp > 0) {
+    smb::nchw_to_nhwc_f32_kernel<<<(unsigned)ceil_div64(Pp * C, 256), 256, 0, st>>>(g, g_nhwc, C, Pp);
+    SMB_LAUNCH_CHECK();
+  }
+  rc = launch_maxpool_bwd_relu(g_nhwc, nullptr, ya, dz, st);
+  if (rc) return rc;
+  rc = launch_act_to_nchw(dz, dx, st);
+  if (rc) return rc;
+  SMB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SMB_OK;
+}
+
+int smb_unit_gram(int impl, const float* f, int C, int H, int W, const float* rowmask, float inv_n, float* G,
+                  void* stream) {
+  SMB_REQUIRE(f && G && C % 64 == 0, "unit_gram: C=%d must be a multiple of 64", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceArena ar;
+  Act a, m;
+  int rc = ar.alloc_act(&a, H, W, C);
+  if (rc) return rc;
+  rc = launch_act_from_nchw(f, a, st);
+  if (rc) return rc;
+  Act src = a;
+  if (rowmask) {
+    rc = ar.alloc_act(&m, H, W, C);
+    if (rc) return rc;
+    rc = launch_mask_rows(a, rowmask, m, st);
+    if (rc) return rc;
+    src = m;
+  }
+  const int ns = gram_num_splits(src.pixels(), C, impl);
+  float* partial = nullptr;
+  rc = ar.alloc(&partial, (int64_t)ns * C * C);
+  if (rc) return rc;
+  rc = gram(impl, src, partial, ns, st);
+  if (rc) return rc;
+  const int64_t CC = (int64_t)C * C;
+  smb::gram_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st>>>(partial, ns, CC,
+                                                                                                inv_n, G);
+  SMB_LAUNCH_CHECK();
+  SMB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SMB_OK;
+}
+
+}  // extern "C"

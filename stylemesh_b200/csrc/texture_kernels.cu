@@ -1,0 +1,263 @@
+// Texture-side kernels: hierarchical bilinear UV sample (forward), UV scatter-add (backward, with the
+// angle/depth gradient-hook weights folded in), fused clamp + L2-regulariser + Adam update, regulariser value.
+//
+// Reference behaviour restated here (never copied):
+//   model/texture/texture.py:41-54   NeuralTexture.normalize()/forward(): clamp to [-123.68,151.061], then
+//                                    F.grid_sample(bilinear, padding_mode='border', align_corners=True)
+//   model/texture/texture.py:96-108  HierarchicalNeuralTexture.forward() = sum over layers; regularizer()
+//   model/model.py:198-202,247-251   gradient hooks  grad *= bilinear(angle_guidance), grad *= depth weight
+//   model/model.py:387-401           torch.optim.Adam(lr, betas (0.9,0.999), eps 1e-8, wd 0)
+// The coordinate arithmetic follows ATen/native/GridSampler.h (grid_sampler_unnormalize, clip_coordinates,
+// within_bounds_2d) operation by operation in fp32 with explicit *_rn intrinsics so that no FMA contraction can
+// change an index:  ix = ((gx + 1) / 2) * (W - 1);  ix = min(W-1, max(ix, 0));  x0 = floor(ix).
+#include "smb_common.cuh"
+#include "smb_kernels.h"
+
+namespace smb {
+
+struct TexCoord {
+  int x0, y0;          // north-west texel
+  float w_nw, w_ne, w_sw, w_se;
+};
+
+__device__ __forceinline__ TexCoord uv_to_texel(float gx, float gy, int W, int H) {
+  // grid_sampler_unnormalize(align_corners=True): ((coord + 1) / 2) * (size - 1)
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+  // clip_coordinates (padding_mode=border): min(size-1, max(in, 0))
+  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+  const float fx = floorf(ix), fy = floorf(iy);
+  TexCoord t;
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  const float x1 = __fadd_rn(fx, 1.f), y1 = __fadd_rn(fy, 1.f);
+  const float ax = __fsub_rn(x1, ix), bx = __fsub_rn(ix, fx);
+  const float ay = __fsub_rn(y1, iy), by = __fsub_rn(iy, fy);
+  t.w_nw = __fmul_rn(ax, ay);
+  t.w_ne = __fmul_rn(bx, ay);
+  t.w_sw = __fmul_rn(ax, by);
+  t.w_se = __fmul_rn(bx, by);
+  return t;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ------------------------------------------------------------------------------------------
+// forward: out[c][p] = sum_l sum_corner w * clamp(tex_l[c][y][x])      one thread per pixel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) uv_sample_fwd_kernel(TexLayerSet tex, const float2* __restrict__ grid,
+                                                            int npix, float clamp_lo, float clamp_hi,
+                                                            float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const float2 g = __ldg(grid + p);
+  float acc[SMB_MAX_TEX_CHANNELS];
+#pragma unroll
+  for (int c = 0; c < SMB_MAX_TEX_CHANNELS; ++c) acc[c] = 0.f;
+  for (int l = 0; l < tex.L; ++l) {
+    const int W = tex.W[l], H = tex.H[l];
+    const TexCoord t = uv_to_texel(g.x, g.y, W, H);
+    const bool x1ok = (t.x0 + 1) < W, y1ok = (t.y0 + 1) < H;   // within_bounds_2d for the +1 corners
+    const size_t plane = (size_t)W * H;
+    const float* base = tex.ptr[l] + (size_t)t.y0 * W + t.x0;
+#pragma unroll
+    for (int c = 0; c < SMB_MAX_TEX_CHANNELS; ++c) {
+      if (c < tex.C) {
+        const float* b = base + c * plane;
+        float v = 0.f;
+        v = fmaf(clampf(__ldg(b), clamp_lo, clamp_hi), t.w_nw, v);
+        if (x1ok) v = fmaf(clampf(__ldg(b + 1), clamp_lo, clamp_hi), t.w_ne, v);
+        if (y1ok) v = fmaf(clampf(__ldg(b + W), clamp_lo, clamp_hi), t.w_sw, v);
+        if (x1ok && y1ok) v = fmaf(clampf(__ldg(b + W + 1), clamp_lo, clamp_hi), t.w_se, v);
+        acc[c] += v;   // torch.stack(...).sum(0): layer results are added in layer order
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < SMB_MAX_TEX_CHANNELS; ++c)
+    if (c < tex.C) out[(size_t)c * npix + p] = acc[c];
+}
+
+// debug/export: the exact integer texel and the four fp32 weights (for the bit-exact index test)
+__global__ void uv_texel_index_kernel(const float2* __restrict__ grid, int npix, int W, int H,
+                                      int* __restrict__ xy0, float* __restrict__ w4) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const float2 g = grid[p];
+  const TexCoord t = uv_to_texel(g.x, g.y, W, H);
+  xy0[2 * p] = t.x0;
+  xy0[2 * p + 1] = t.y0;
+  w4[4 * p] = t.w_nw;
+  w4[4 * p + 1] = t.w_ne;
+  w4[4 * p + 2] = t.w_sw;
+  w4[4 * p + 3] = t.w_se;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: gtex_l[c][y][x] += w_corner * (gout[c][p] * hook0[p] * hook1[p])
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) uv_scatter_bwd_kernel(TexLayerSet gtex, const float2* __restrict__ grid,
+                                                             int npix, const float* __restrict__ gout,
+                                                             const float* __restrict__ hook0,
+                                                             const float* __restrict__ hook1) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float g[SMB_MAX_TEX_CHANNELS];
+  // hooks run in registration order: angle first (model.py:195-202), then depth (model.py:245-251);
+  // autograd applies them most-recent-last == same order, one fp32 multiply each.
+  bool any = false;
+#pragma unroll
+  for (int c = 0; c < SMB_MAX_TEX_CHANNELS; ++c) {
+    g[c] = 0.f;
+    if (c < gtex.C) {
+      float v = __ldg(gout + (size_t)c * npix + p);
+      if (hook0) v = __fmul_rn(v, __ldg(hook0 + p));
+      if (hook1) v = __fmul_rn(v, __ldg(hook1 + p));
+      g[c] = v;
+      any |= (v != 0.f);
+    }
+  }
+  if (!any) return;
+  const float2 uv = __ldg(grid + p);
+  for (int l = 0; l < gtex.L; ++l) {
+    const int W = gtex.W[l], H = gtex.H[l];
+    const TexCoord t = uv_to_texel(uv.x, uv.y, W, H);
+    const bool x1ok = (t.x0 + 1) < W, y1ok = (t.y0 + 1) < H;
+    const size_t plane = (size_t)W * H;
+    float* base = gtex.ptr[l] + (size_t)t.y0 * W + t.x0;
+#pragma unroll
+    for (int c = 0; c < SMB_MAX_TEX_CHANNELS; ++c) {
+      if (c < gtex.C && g[c] != 0.f) {
+        float* b = base + c * plane;
+        atomicAdd(b, __fmul_rn(t.w_nw, g[c]));
+        if (x1ok) atomicAdd(b + 1, __fmul_rn(t.w_ne, g[c]));
+        if (y1ok) atomicAdd(b + W, __fmul_rn(t.w_sw, g[c]));
+        if (x1ok && y1ok) atomicAdd(b + W + 1, __fmul_rn(t.w_se, g[c]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused Adam:  x = clamp(p);  g' = g*gscale + reg*x;  m,v update;  p = x - step;  g = 0
+// (torch/optim/adam.py single-tensor path: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g,g,1-b2);
+//  denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1))
+// ------------------------------------------------------------------------------------------
+struct AdamScalars {
+  float one_minus_b1, b2, one_minus_b2, inv_sqrt_bc2, eps, neg_step;
+  float clamp_lo, clamp_hi, reg_coef, gscale;
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float& g, float& m, float& v, const AdamScalars& s) {
+  const float x = clampf(p, s.clamp_lo, s.clamp_hi);
+  const float gg = fmaf(s.reg_coef, x, g * s.gscale);
+  m = fmaf(s.one_minus_b1, gg - m, m);
+  v = fmaf(s.one_minus_b2 * gg, gg, v * s.b2);
+  const float denom = sqrtf(v) * s.inv_sqrt_bc2 + s.eps;
+  p = fmaf(s.neg_step, m / denom, x);
+  g = 0.f;
+}
+
+__global__ void __launch_bounds__(256) adam_clamp_reg_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                             float* __restrict__ m, float* __restrict__ v,
+                                                             int64_t n, AdamScalars s) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    adam_elem(P.x, G.x, M.x, V.x, s);
+    adam_elem(P.y, G.y, M.y, V.y, s);
+    adam_elem(P.z, G.z, M.z, V.z, s);
+    adam_elem(P.w, G.w, M.w, V.w, s);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(g)[i] = G;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // tail (n not a multiple of 4)
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_elem(p[i], g[i], m[i], v[i], s);
+}
+
+// regulariser value:  out += coef * sum(clamp(x)^2)     (coef = lambda * w_l / N_l)
+__global__ void __launch_bounds__(256) sumsq_clamped_kernel(const float* __restrict__ x, int64_t n, float coef,
+                                                            float clamp_lo, float clamp_hi,
+                                                            float* __restrict__ out) {
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float c = clampf(x[i], clamp_lo, clamp_hi);
+    acc = fmaf(c, c, acc);
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc * coef);
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+int launch_uv_sample_fwd(const TexLayerSet& tex, const float* grid, int H, int W, float clamp_lo, float clamp_hi,
+                         float* out, cudaStream_t st) {
+  const int npix = H * W;
+  if (npix == 0) return SMB_OK;
+  uv_sample_fwd_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(tex, reinterpret_cast<const float2*>(grid), npix,
+                                                           clamp_lo, clamp_hi, out);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int launch_uv_texel_index(const float* grid, int npix, int W, int H, int* xy0, float* w4, cudaStream_t st) {
+  if (npix == 0) return SMB_OK;
+  uv_texel_index_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(grid), npix, W, H,
+                                                            xy0, w4);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int launch_uv_scatter_bwd(const TexLayerSet& gtex, const float* grid, int H, int W, const float* gout,
+                          const float* hook0, const float* hook1, cudaStream_t st) {
+  const int npix = H * W;
+  if (npix == 0) return SMB_OK;
+  uv_scatter_bwd_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(gtex, reinterpret_cast<const float2*>(grid), npix,
+                                                            gout, hook0, hook1);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int launch_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                int step, float clamp_lo, float clamp_hi, float reg_coef, float gscale, cudaStream_t st) {
+  if (n == 0) return SMB_OK;
+  SMB_REQUIRE(step >= 1, "adam: step must be >= 1 (got %d)", step);
+  // scalar prep in double, as python floats are in torch/optim/adam.py
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  AdamScalars s;
+  s.one_minus_b1 = (float)(1.0 - (double)beta1);
+  s.b2 = beta2;
+  s.one_minus_b2 = (float)(1.0 - (double)beta2);
+  s.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  s.eps = eps;
+  s.neg_step = (float)(-(double)lr / bc1);
+  s.clamp_lo = clamp_lo;
+  s.clamp_hi = clamp_hi;
+  s.reg_coef = reg_coef;
+  s.gscale = gscale;
+  const int64_t n4 = (n + 3) >> 2;
+  int blocks = (int)std::min<int64_t>(ceil_div64(n4, 256), (int64_t)148 * 16);
+  adam_clamp_reg_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, s);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int launch_sumsq_clamped(const float* x, int64_t n, float coef, float clamp_lo, float clamp_hi, float* out,
+                         cudaStream_t st) {
+  if (n == 0) return SMB_OK;
+  int blocks = (int)std::min<int64_t>(ceil_div64(n, 256 * 8), (int64_t)148 * 8);
+  sumsq_clamped_kernel<<<blocks, 256, 0, st>>>(x, n, coef, clamp_lo, clamp_hi, out);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+}  // namespace smb
