@@ -1,0 +1,28 @@
+"""pytest configuration: the `gpu` marker (tests that need a real B200) and import paths."""
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this environment")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
