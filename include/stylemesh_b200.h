@@ -97,6 +97,12 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
 int smb_level_feature_shape(smb_ctx* ctx, int slot, int conv, int* C, int* h, int* w);
 int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, void* stream);
 
+/* Export relu(conv_i) as fp32 channels-last (h*w, C) — the layout smb_level_content_term takes its target in. */
+int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc, void* stream);
+
+/* Free every slot's device memory (e.g. after the one-off style-target pass over large style images). */
+int smb_ctx_release_slots(smb_ctx* ctx);
+
 /* Masked Gram of relu(conv_i):  G = inv_n * sum_p m_p F_p F_p^T  -> gram_out (C x C fp32). rowmask may be NULL. */
 int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, float* gram_out,
                    void* stream);

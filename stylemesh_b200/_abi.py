@@ -40,6 +40,8 @@ PROTOTYPES = [
     ("smb_level_forward", _i, [_p, _i, _p, _i, _p]),
     ("smb_level_feature_shape", _i, [_p, _i, _i, _ip, _ip, _ip]),
     ("smb_level_get_feature", _i, [_p, _i, _i, _p, _p]),
+    ("smb_level_get_feature_nhwc", _i, [_p, _i, _i, _p, _p]),
+    ("smb_ctx_release_slots", _i, [_p]),
     ("smb_level_gram", _i, [_p, _i, _i, _p, _f, _p, _p]),
     ("smb_level_style_term", _i, [_p, _i, _i, _p, _f, _p, _f, _p, _f, _p, _f, _p, _p, _p]),
     ("smb_level_content_term", _i, [_p, _i, _i, _p, _p, _f, _f, _p, _p]),

@@ -427,6 +427,38 @@ int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, voi
   return launch_act_to_nchw(sp->y[conv], out_nchw, (cudaStream_t)stream);
 }
 
+namespace smb {
+__global__ void act_to_f32_kernel(Act src, float* __restrict__ dst) {
+  const int64_t n2 = src.elems() >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const uint32_t h = reinterpret_cast<const uint32_t*>(src.hi)[i];
+    const uint32_t l = reinterpret_cast<const uint32_t*>(src.lo)[i];
+    reinterpret_cast<float2*>(dst)[i] = make_float2(bf16lo_to_f(h) + bf16lo_to_f(l), bf16hi_to_f(h) + bf16hi_to_f(l));
+  }
+}
+}  // namespace smb
+
+int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc, void* stream) {
+  Slot* sp = get_slot(ctx, slot);
+  if (!sp) return SMB_ERR_ARG;
+  SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && out_nhwc, "get_feature_nhwc: conv %d not computed (last=%d)",
+              conv, sp->last_done);
+  const Act& a = sp->y[conv];
+  if (a.elems() == 0) return SMB_OK;
+  smb::act_to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1, 256), 148 * 16), 256, 0,
+                           (cudaStream_t)stream>>>(a, out_nhwc);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int smb_ctx_release_slots(smb_ctx* ctx) {
+  SMB_REQUIRE(ctx, "null context");
+  SMB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->slots.clear();
+  return SMB_OK;
+}
+
 int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, float* gram_out,
                    void* stream) {
   Slot* sp = get_slot(ctx, slot);

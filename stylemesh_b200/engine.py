@@ -1,0 +1,288 @@
+"""Thin Python handles over the C-ABI (include/stylemesh_b200.h): texture ops and the VGG/loss engine.
+
+torch is used for device memory, streams and tiny shape glue only; every arithmetic step of the hot path is a
+kernel in libstylemesh_b200.so.  Nothing here falls back to torch ops or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _abi
+
+CLAMP_LO, CLAMP_HI = -123.6800, 151.0610     # model/texture/texture.py:43
+
+# relu(conv) names of model/losses/content_and_style_losses.py:49-66 -> index into the 13-conv table
+LAYER_INDEX = {"r11": 0, "r12": 1, "r21": 2, "r22": 3, "r31": 4, "r32": 5, "r33": 6, "r34": 7,
+               "r41": 8, "r42": 9, "r43": 10, "r44": 11, "r51": 12}
+CONV_NAMES = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv3_4",
+              "conv4_1", "conv4_2", "conv4_3", "conv4_4", "conv5_1"]
+CONV_COUT = [64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512]
+
+
+def layer_index(name: str) -> int:
+    if name not in LAYER_INDEX:
+        raise ValueError(f"Unsupported VGG layer '{name}': the B200 engine computes relu outputs r11..r51 "
+                         f"({sorted(LAYER_INDEX)})")
+    return LAYER_INDEX[name]
+
+
+def require_cuda_device(device) -> None:
+    if torch.device(device).type != "cuda":
+        raise _abi.StyleMeshB200Error(
+            f"tensors live on '{device}': move the module to a CUDA device (model.cuda()); stylemesh_b200 has no CPU path")
+
+
+def _require_cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _abi.StyleMeshB200Error(f"{what} must be a CUDA tensor: stylemesh_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# texture ops
+# ---------------------------------------------------------------------------------------------------------------
+def uv_sample_fwd(layers: Sequence[torch.Tensor], grid: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  clamp=(CLAMP_LO, CLAMP_HI)) -> torch.Tensor:
+    """layers: list of (C,H_l,W_l); grid (h,w,2) -> out (C,h,w).  (texture.py:46-54, 96-100)"""
+    lib = _abi.load()
+    layers = [_require_cuda_f32(t, "texture layer") for t in layers]
+    grid = _require_cuda_f32(grid, "uv grid")
+    h, w = grid.shape[-3], grid.shape[-2]
+    c = layers[0].shape[0]
+    if out is None:
+        out = torch.empty((c, h, w), device=grid.device, dtype=torch.float32)
+    rc = lib.smb_uv_sample_fwd(_abi.ptr_array(layers), _abi.int_array([t.shape[2] for t in layers]),
+                               _abi.int_array([t.shape[1] for t in layers]), len(layers), c, _abi.ptr(grid), h, w,
+                               clamp[0], clamp[1], _abi.ptr(out), _abi.current_stream())
+    _abi.check(rc, "smb_uv_sample_fwd")
+    return out
+
+
+def uv_texel_index(grid: torch.Tensor, tex_w: int, tex_h: int):
+    lib = _abi.load()
+    grid = _require_cuda_f32(grid, "uv grid")
+    n = grid.numel() // 2
+    xy0 = torch.empty((n, 2), device=grid.device, dtype=torch.int32)
+    w4 = torch.empty((n, 4), device=grid.device, dtype=torch.float32)
+    _abi.check(lib.smb_uv_texel_index(_abi.ptr(grid), n, tex_w, tex_h, _abi.ptr(xy0), _abi.ptr(w4),
+                                      _abi.current_stream()), "smb_uv_texel_index")
+    return xy0, w4
+
+
+def uv_scatter_bwd(grad_layers: Sequence[torch.Tensor], grid: torch.Tensor, grad_out: torch.Tensor,
+                   hook0: Optional[torch.Tensor] = None, hook1: Optional[torch.Tensor] = None) -> None:
+    """grad_layers[l] (C,H_l,W_l) += scatter(grad_out (C,h,w) * hook0 * hook1)   (accumulates)."""
+    lib = _abi.load()
+    for t in grad_layers:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("gradient layers must be contiguous CUDA float32 tensors (they are written in place)")
+    grid = _require_cuda_f32(grid, "uv grid")
+    grad_out = _require_cuda_f32(grad_out, "grad_out")
+    h, w = grid.shape[-3], grid.shape[-2]
+    c = grad_layers[0].shape[0]
+    hook0 = None if hook0 is None else _require_cuda_f32(hook0, "hook0")
+    hook1 = None if hook1 is None else _require_cuda_f32(hook1, "hook1")
+    rc = lib.smb_uv_scatter_bwd(_abi.ptr_array(grad_layers), _abi.int_array([t.shape[2] for t in grad_layers]),
+                                _abi.int_array([t.shape[1] for t in grad_layers]), len(grad_layers), c,
+                                _abi.ptr(grid), h, w, _abi.ptr(grad_out), _abi.ptr(hook0), _abi.ptr(hook1),
+                                _abi.current_stream())
+    _abi.check(rc, "smb_uv_scatter_bwd")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, reg_coef=0.0, grad_scale=1.0,
+              clamp=(CLAMP_LO, CLAMP_HI)) -> None:
+    lib = _abi.load()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("adam_step operates in place on contiguous CUDA float32 tensors")
+    rc = lib.smb_adam_step(_abi.ptr(param), _abi.ptr(grad), _abi.ptr(exp_avg), _abi.ptr(exp_avg_sq), param.numel(),
+                           lr, beta1, beta2, eps, int(step), clamp[0], clamp[1], reg_coef, grad_scale,
+                           _abi.current_stream())
+    _abi.check(rc, "smb_adam_step")
+
+
+def texreg_value(param: torch.Tensor, coef: float, out_accum: torch.Tensor, clamp=(CLAMP_LO, CLAMP_HI)) -> None:
+    lib = _abi.load()
+    rc = lib.smb_texreg_value(_abi.ptr(param), param.numel(), coef, clamp[0], clamp[1], _abi.ptr(out_accum),
+                              _abi.current_stream())
+    _abi.check(rc, "smb_texreg_value")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VGG / loss engine
+# ---------------------------------------------------------------------------------------------------------------
+def _impl_from_env(name: str, default: int) -> int:
+    v = os.environ.get(name, "").strip().lower()
+    if v in ("", "default"):
+        return default
+    if v in ("tc", "tcgen05", "1"):
+        return _abi.IMPL_TC
+    if v in ("simt", "0"):
+        return _abi.IMPL_SIMT
+    raise ValueError(f"{name}={v!r}: expected 'tc' or 'simt'")
+
+
+class VGGEngine:
+    """Owns an smb_ctx: frozen VGG-19 conv1_1..conv5_1 in kernel layout + per-resolution working sets."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], conv_impl: Optional[int] = None,
+                 gram_impl: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _abi.StyleMeshB200Error("VGGEngine needs a CUDA device: stylemesh_b200 has no CPU path")
+        self._lib = _abi.load()
+        torch.cuda.current_device()          # make sure the primary context exists and is current
+        torch.zeros(1, device="cuda")
+        self._ctx = self._lib.smb_ctx_create()
+        if not self._ctx:
+            raise _abi.StyleMeshB200Error(f"smb_ctx_create failed: {_abi.last_error()}")
+        self.conv_impl = _impl_from_env("SMB_CONV_IMPL", _abi.IMPL_TC) if conv_impl is None else conv_impl
+        self.gram_impl = _impl_from_env("SMB_GRAM_IMPL", _abi.IMPL_TC) if gram_impl is None else gram_impl
+        _abi.check(self._lib.smb_ctx_set_impl(self._ctx, self.conv_impl, self.gram_impl), "smb_ctx_set_impl")
+        ws, bs = [], []
+        for name in CONV_NAMES:
+            ws.append(state_dict[name + ".weight"].detach().to("cpu", torch.float32).contiguous())
+            bs.append(state_dict[name + ".bias"].detach().to("cpu", torch.float32).contiguous())
+        _abi.check(self._lib.smb_ctx_load_vgg(self._ctx, _abi.ptr_array(ws), _abi.ptr_array(bs), len(ws)),
+                   "smb_ctx_load_vgg")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.smb_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- slots --------------------------------------------------------------------------------------------
+    def begin(self, H: int, W: int) -> int:
+        return _abi.check(self._lib.smb_level_begin(self._ctx, int(H), int(W)), "smb_level_begin")
+
+    def release_slots(self) -> None:
+        _abi.check(self._lib.smb_ctx_release_slots(self._ctx), "smb_ctx_release_slots")
+
+    def device_bytes(self) -> int:
+        return int(self._lib.smb_ctx_device_bytes(self._ctx))
+
+    # -- forward / features ---------------------------------------------------------------------------------
+    def forward(self, slot: int, image: torch.Tensor, last_conv: int) -> None:
+        image = _require_cuda_f32(image, "image")
+        _abi.check(self._lib.smb_level_forward(self._ctx, slot, _abi.ptr(image), int(last_conv),
+                                               _abi.current_stream()), "smb_level_forward")
+
+    def feature_shape(self, slot: int, conv: int):
+        c, h, w = C.c_int(), C.c_int(), C.c_int()
+        _abi.check(self._lib.smb_level_feature_shape(self._ctx, slot, conv, C.byref(c), C.byref(h), C.byref(w)),
+                   "smb_level_feature_shape")
+        return c.value, h.value, w.value
+
+    def feature(self, slot: int, conv: int) -> torch.Tensor:
+        c, h, w = self.feature_shape(slot, conv)
+        out = torch.empty((c, h, w), device=self.device, dtype=torch.float32)
+        _abi.check(self._lib.smb_level_get_feature(self._ctx, slot, conv, _abi.ptr(out), _abi.current_stream()),
+                   "smb_level_get_feature")
+        return out
+
+    def feature_nhwc(self, slot: int, conv: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        c, h, w = self.feature_shape(slot, conv)
+        if out is None:
+            out = torch.empty((h * w, c), device=self.device, dtype=torch.float32)
+        _abi.check(self._lib.smb_level_get_feature_nhwc(self._ctx, slot, conv, _abi.ptr(out),
+                                                        _abi.current_stream()), "smb_level_get_feature_nhwc")
+        return out
+
+    def gram(self, slot: int, conv: int, rowmask: Optional[torch.Tensor], inv_n: float) -> torch.Tensor:
+        c = CONV_COUT[conv]
+        out = torch.empty((c, c), device=self.device, dtype=torch.float32)
+        _abi.check(self._lib.smb_level_gram(self._ctx, slot, conv, _abi.ptr(rowmask), float(inv_n), _abi.ptr(out),
+                                            _abi.current_stream()), "smb_level_gram")
+        return out
+
+    # -- loss terms / backward ------------------------------------------------------------------------------
+    def style_term(self, slot: int, conv: int, rowmask: Optional[torch.Tensor], inv_n: float,
+                   target0: torch.Tensor, coef0: float, target1: Optional[torch.Tensor], coef1: float,
+                   loss_accum: torch.Tensor, prev_sum: Optional[torch.Tensor] = None, avg_len: float = 1.0,
+                   gram_out: Optional[torch.Tensor] = None) -> None:
+        _abi.check(self._lib.smb_level_style_term(self._ctx, slot, conv, _abi.ptr(rowmask), float(inv_n),
+                                                  _abi.ptr(target0), float(coef0), _abi.ptr(target1), float(coef1),
+                                                  _abi.ptr(prev_sum), float(avg_len), _abi.ptr(gram_out),
+                                                  _abi.ptr(loss_accum), _abi.current_stream()),
+                   "smb_level_style_term")
+
+    def content_term(self, slot: int, conv: int, target_nhwc: torch.Tensor, rowmask: torch.Tensor,
+                     coef_loss: float, coef_grad: float, loss_accum: torch.Tensor) -> None:
+        _abi.check(self._lib.smb_level_content_term(self._ctx, slot, conv, _abi.ptr(target_nhwc), _abi.ptr(rowmask),
+                                                    float(coef_loss), float(coef_grad), _abi.ptr(loss_accum),
+                                                    _abi.current_stream()), "smb_level_content_term")
+
+    def backward(self, slot: int, H: int, W: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty((3, H, W), device=self.device, dtype=torch.float32)
+        _abi.check(self._lib.smb_level_backward(self._ctx, slot, _abi.ptr(out), _abi.current_stream()),
+                   "smb_level_backward")
+        return out
+
+    # -- whole-network convenience (VGG.forward of the reference) --------------------------------------------
+    def features(self, image: torch.Tensor, keys: Sequence[str]) -> Dict[str, torch.Tensor]:
+        """image (3,H,W) or (1,3,H,W) -> {key: (1,C,h,w)}"""
+        img = image[0] if image.dim() == 4 else image
+        idx = [layer_index(k) for k in keys]
+        slot = self.begin(img.shape[1], img.shape[2])
+        self.forward(slot, img, max(idx))
+        return {k: self.feature(slot, i).unsqueeze(0) for k, i in zip(keys, idx)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# unit-level wrappers (parity tests)
+# ---------------------------------------------------------------------------------------------------------------
+def unit_conv3x3(impl: int, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool,
+                 transpose_flip: bool = False) -> torch.Tensor:
+    lib = _abi.load()
+    x = _require_cuda_f32(x, "x")
+    cout, cin = w.shape[0], w.shape[1]
+    _, H, W = x.shape
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    bc = None if b is None else b.detach().to("cpu", torch.float32).contiguous()
+    y = torch.empty((cin if transpose_flip else cout, H, W), device=x.device, dtype=torch.float32)
+    _abi.check(lib.smb_unit_conv3x3(impl, _abi.ptr(x), cin, H, W, _abi.ptr(wc), _abi.ptr(bc), cout, int(relu),
+                                    int(transpose_flip), _abi.ptr(y), _abi.current_stream()), "smb_unit_conv3x3")
+    return y
+
+
+def unit_maxpool(x: torch.Tensor) -> torch.Tensor:
+    lib = _abi.load()
+    x = _require_cuda_f32(x, "x")
+    c, H, W = x.shape
+    y = torch.empty((c, H // 2, W // 2), device=x.device, dtype=torch.float32)
+    _abi.check(lib.smb_unit_maxpool(_abi.ptr(x), c, H, W, _abi.ptr(y), _abi.current_stream()), "smb_unit_maxpool")
+    return y
+
+
+def unit_maxpool_bwd(g: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    lib = _abi.load()
+    g = _require_cuda_f32(g, "g")
+    y = _require_cuda_f32(y, "y")
+    c, H, W = y.shape
+    dx = torch.empty_like(y)
+    _abi.check(lib.smb_unit_maxpool_bwd(_abi.ptr(g), _abi.ptr(y), c, H, W, _abi.ptr(dx), _abi.current_stream()),
+               "smb_unit_maxpool_bwd")
+    return dx
+
+
+def unit_gram(impl: int, f: torch.Tensor, rowmask: Optional[torch.Tensor], inv_n: float) -> torch.Tensor:
+    lib = _abi.load()
+    f = _require_cuda_f32(f, "f")
+    c, H, W = f.shape
+    G = torch.empty((c, c), device=f.device, dtype=torch.float32)
+    _abi.check(lib.smb_unit_gram(impl, _abi.ptr(f), c, H, W, _abi.ptr(rowmask), float(inv_n), _abi.ptr(G),
+                                 _abi.current_stream()), "smb_unit_gram")
+    return G

@@ -1,0 +1,155 @@
+"""A CPU emulation of the C-ABI engine's SEMANTICS (include/stylemesh_b200.h) built from the oracle's torch ops.
+TEST INFRASTRUCTURE: it lets the host-side logic of the product (loss plan, coefficients, fused-state plumbing,
+optimizer, DDP scaling) be checked against the golden fixtures in the GPU-less container.  It is monkeypatched in
+by tests only; the product has no way to select it."""
+import torch
+import torch.nn.functional as F
+
+from oracle import stylemesh_oracle as orc
+
+CLAMP = (orc.CLAMP_LO, orc.CLAMP_HI)
+KEYS = ["r11", "r12", "r21", "r22", "r31", "r32", "r33", "r34", "r41", "r42", "r43", "r44", "r51"]
+
+
+def uv_sample_fwd(layers, grid, out=None, clamp=CLAMP):
+    ls = [l.detach().clamp(*clamp) for l in layers]
+    ys = [F.grid_sample(l.unsqueeze(0), grid.unsqueeze(0), mode="bilinear", padding_mode="border",
+                        align_corners=True)[0] for l in ls]
+    return torch.stack(ys).sum(0)
+
+
+def uv_scatter_bwd(grad_layers, grid, grad_out, hook0=None, hook1=None):
+    g = grad_out.clone()
+    if hook0 is not None:
+        g = g * hook0.reshape(1, *g.shape[1:])
+    if hook1 is not None:
+        g = g * hook1.reshape(1, *g.shape[1:])
+    for gl in grad_layers:
+        z = torch.zeros_like(gl).requires_grad_(True)
+        y = F.grid_sample(z.unsqueeze(0), grid.unsqueeze(0), mode="bilinear", padding_mode="border",
+                          align_corners=True)[0]
+        (dz,) = torch.autograd.grad(y, z, g)
+        gl += dz
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, reg_coef=0.0, grad_scale=1.0,
+              clamp=CLAMP):
+    x = param.clamp(*clamp)
+    g = grad * grad_scale + reg_coef * x
+    exp_avg.lerp_(g, 1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    denom = exp_avg_sq.sqrt() / (bc2 ** 0.5) + eps
+    param.copy_(x - (lr / bc1) * exp_avg / denom)
+    grad.zero_()
+
+
+def texreg_value(param, coef, out_accum, clamp=CLAMP):
+    out_accum += coef * (param.clamp(*clamp) ** 2).sum()
+
+
+def unit_gram(impl, f, rowmask, inv_n):
+    fl = f.reshape(f.shape[0], -1)
+    if rowmask is not None:
+        fl = fl * rowmask.reshape(1, -1)
+    return fl @ fl.t() * inv_n
+
+
+class VGGEngine:
+    def __init__(self, state_dict, conv_impl=None, gram_impl=None):
+        self.sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+        self.slots = []
+        self.device = torch.device("cpu")
+
+    def close(self):
+        pass
+
+    def begin(self, H, W):
+        for i, s in enumerate(self.slots):
+            if s["size"] == (H, W):
+                return i
+        self.slots.append({"size": (H, W)})
+        return len(self.slots) - 1
+
+    def release_slots(self):
+        self.slots = []
+
+    def forward(self, slot, image, last_conv):
+        s = self.slots[slot]
+        with torch.enable_grad():            # the product may call us from inside an autograd.Function (no-grad mode)
+            img = image.detach().clone().requires_grad_(True)
+            feats = orc.vgg_forward(self.sd, img.unsqueeze(0), KEYS[:last_conv + 1], as_written=False)
+        s.update(img=img, feats=feats, pend={}, last=last_conv)
+
+    def feature_shape(self, slot, conv):
+        f = self.slots[slot]["feats"][KEYS[conv]]
+        return f.shape[1], f.shape[2], f.shape[3]
+
+    def feature(self, slot, conv):
+        return self.slots[slot]["feats"][KEYS[conv]][0].detach().clone()
+
+    def feature_nhwc(self, slot, conv, out=None):
+        f = self.feature(slot, conv)
+        return f.permute(1, 2, 0).reshape(-1, f.shape[0]).contiguous()
+
+    def features(self, image, keys):
+        img = image[0] if image.dim() == 4 else image
+        return {k: v.detach() for k, v in orc.vgg_forward(self.sd, img.unsqueeze(0), keys, as_written=False).items()}
+
+    def _masked(self, slot, conv, rowmask):
+        f = self.slots[slot]["feats"][KEYS[conv]][0].detach()
+        fl = f.reshape(f.shape[0], -1)
+        return fl * rowmask.reshape(1, -1) if rowmask is not None else fl
+
+    def gram(self, slot, conv, rowmask, inv_n):
+        fl = self._masked(slot, conv, rowmask)
+        return fl @ fl.t() * inv_n
+
+    def style_term(self, slot, conv, rowmask, inv_n, target0, coef0, target1, coef1, loss_accum, prev_sum=None,
+                   avg_len=1.0, gram_out=None):
+        fl = self._masked(slot, conv, rowmask)
+        G = fl @ fl.t() * inv_n
+        if gram_out is not None:
+            gram_out.copy_(G)
+        ghat = G if prev_sum is None else (G + prev_sum) / avg_len
+        ln = avg_len if prev_sum is not None else 1.0
+        C = G.shape[0]
+        d = coef0 * (ghat - target0)
+        loss_accum += coef0 * ((ghat - target0) ** 2).mean()
+        if target1 is not None:
+            d = d + coef1 * (ghat - target1)
+            loss_accum += coef1 * ((ghat - target1) ** 2).mean()
+        if inv_n == 0:
+            return
+        bmat = (2 * inv_n / ln) * (2 * d / (C * C))
+        df = (bmat @ fl)                      # Bmat symmetric: dF[c][p] = sum_k B[c][k] Fm[k][p]
+        s = self.slots[slot]
+        s["pend"][conv] = s["pend"].get(conv, 0) + df.reshape(self.slots[slot]["feats"][KEYS[conv]][0].shape)
+
+    def content_term(self, slot, conv, target_nhwc, rowmask, coef_loss, coef_grad, loss_accum):
+        f = self.slots[slot]["feats"][KEYS[conv]][0].detach()
+        t = target_nhwc.reshape(f.shape[1], f.shape[2], f.shape[0]).permute(2, 0, 1)
+        m = rowmask.reshape(1, f.shape[1], f.shape[2])
+        d = (f - t) * m
+        loss_accum += coef_loss * (d ** 2).sum()
+        s = self.slots[slot]
+        s["pend"][conv] = s["pend"].get(conv, 0) + coef_grad * d
+
+    def backward(self, slot, H, W, out=None):
+        s = self.slots[slot]
+        if not s["pend"]:
+            return torch.zeros(3, H, W)
+        with torch.enable_grad():
+            total = sum((s["feats"][KEYS[c]][0] * g).sum() for c, g in s["pend"].items())
+            (gi,) = torch.autograd.grad(total, s["img"], retain_graph=True)
+        s["pend"] = {}
+        return gi
+
+
+def install(monkeypatch):
+    """Route the product's engine calls to the emulation (tests only)."""
+    from stylemesh_b200 import engine
+    from stylemesh_b200.model import model as pm
+    for name in ["uv_sample_fwd", "uv_scatter_bwd", "adam_step", "texreg_value", "unit_gram", "VGGEngine"]:
+        monkeypatch.setattr(engine, name, globals()[name])
+    monkeypatch.setattr(engine, "require_cuda_device", lambda dev: None)

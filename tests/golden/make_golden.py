@@ -141,7 +141,7 @@ def run_reference(spec):
             for p, t in zip(params, layers):
                 p.copy_(t)
         (opt,), _ = mdl.configure_optimizers()
-        traj = []
+        traj, states = [], []
         for i in range(spec["steps"]):
             opt.zero_grad()
             res = mdl.training_step(batch, i)
@@ -149,7 +149,12 @@ def run_reference(spec):
             opt.step()
             traj.append({k: float(mdl.loss_history[k]["train"][-1].reshape(-1)[0]) for k in
                          ["content", "style", "tex_reg", "total"]})
+            # optimiser state after step i: lets a test replay step i+1 teacher-forced from the reference's state
+            states.append({"params": [p.detach().clone() for p in params],
+                           "exp_avg": [opt.state[p]["exp_avg"].clone() for p in params],
+                           "exp_avg_sq": [opt.state[p]["exp_avg_sq"].clone() for p in params]})
         out["traj"] = traj
+        out["states"] = states
         out["final_layers"] = [p.detach().clone() for p in params]
     return out
 

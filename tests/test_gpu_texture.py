@@ -1,0 +1,120 @@
+"""GPU parity of the texture-side kernels (through the C-ABI) against the CPU oracle / torch fp32 CPU ops."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stylemesh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng():
+    from stylemesh_b200 import engine
+    return engine
+
+
+def _grid(seed, h, w):
+    g = torch.Generator().manual_seed(seed)
+    grid = torch.rand(h, w, 2, generator=g) * 2.2 - 1.1             # includes out-of-range coordinates
+    grid[0, 0] = torch.tensor([-1.0, -1.0])                         # the "invalid pixel" value
+    grid[0, 1] = torch.tensor([1.0, 1.0])
+    grid[0, 2] = torch.tensor([1.0 - 1e-7, -1.0 + 1e-7])
+    grid[0, 3] = torch.tensor([0.0, 0.0])
+    return grid
+
+
+@pytest.mark.parametrize("tex_wh", [(37, 23), (512, 512), (2048, 2048)])
+def test_uv_index_math_bit_exact(tex_wh):
+    """north_star: bit-exact UV index math — integer texels AND the fp32 weights equal the ATen formula."""
+    eng = _eng()
+    W, H = tex_wh
+    grid = _grid(1, 61, 67)
+    # exact texel centres as well
+    xs = torch.arange(0, 8, dtype=torch.float32) / (W - 1) * 2 - 1
+    grid[1, :8, 0] = xs
+    x0, y0, w = orc.uv_texel_indices_np(grid.numpy(), W, H)
+    xy_d, w_d = eng.uv_texel_index(grid.cuda(), W, H)
+    xy_d = xy_d.cpu().numpy().reshape(61, 67, 2)
+    assert np.array_equal(xy_d[..., 0], x0) and np.array_equal(xy_d[..., 1], y0)
+    assert np.array_equal(w_d.cpu().numpy().reshape(61, 67, 4).view(np.uint32), w.view(np.uint32))
+
+
+@pytest.mark.parametrize("num_layers", [1, 4])
+def test_sample_forward_matches_grid_sample(num_layers):
+    eng = _eng()
+    g = torch.Generator().manual_seed(3)
+    layers = [torch.rand(3, 96 // 2 ** i, 128 // 2 ** i, generator=g) * 300 - 150 for i in range(num_layers)]
+    grid = _grid(2, 45, 53)
+    ref = orc.texture_sample([l.clone() for l in layers], grid.unsqueeze(0))[0]      # clamps, then samples
+    out = eng.uv_sample_fwd([l.cuda() for l in layers], grid.cuda()).cpu()
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_scatter_backward_matches_autograd_with_hooks():
+    eng = _eng()
+    g = torch.Generator().manual_seed(5)
+    layers = [torch.rand(3, 64 // 2 ** i, 80 // 2 ** i, generator=g).requires_grad_(True) for i in range(3)]
+    grid = _grid(4, 33, 47)
+    gout = torch.randn(3, 33, 47, generator=g)
+    hook0 = torch.rand(33, 47, generator=g)
+    hook1 = torch.rand(33, 47, generator=g)
+    out = orc.texture_sample(layers, grid.unsqueeze(0))
+    out.backward((gout * hook0 * hook1).unsqueeze(0))
+    grads = [torch.zeros_like(l).cuda() for l in layers]
+    eng.uv_scatter_bwd(grads, grid.cuda(), gout.cuda(), hook0.cuda(), hook1.cuda())
+    for gd, l in zip(grads, layers):
+        assert (gd.cpu() - l.grad).norm() <= 1e-5 * l.grad.norm() + 1e-7
+
+
+def test_full_size_partition_of_unity():
+    """size-independent properties at the benchmark shape (2048^2 x 4 layers, 640x480 view)."""
+    eng = _eng()
+    from stylemesh_b200 import synthetic as syn
+    view = syn.make_view(1000, (480, 640), [(480, 640)])
+    grid = view.uvs[0][0].cuda()
+    layers = [torch.full((3, 2048 // 2 ** i, 2048 // 2 ** i), float(i + 1), device="cuda") for i in range(4)]
+    out = eng.uv_sample_fwd(layers, grid)
+    assert torch.allclose(out, torch.full_like(out, 10.0), rtol=0, atol=1e-4)      # weights sum to 1 per layer
+    gout = torch.rand(3, 480, 640, device="cuda")
+    grads = [torch.zeros_like(l) for l in layers]
+    eng.uv_scatter_bwd(grads, grid, gout, None, None)
+    want = gout.double().sum(dim=(1, 2))
+    for gl in grads:
+        got = gl.double().sum(dim=(1, 2))
+        assert torch.allclose(got, want, rtol=1e-4)
+
+
+def test_fused_adam_clamp_reg_matches_torch():
+    eng = _eng()
+    g = torch.Generator().manual_seed(9)
+    n = 3 * 33 * 35                                      # not a multiple of 4: exercises the scalar tail
+    p0 = torch.rand(n, generator=g) * 400 - 200          # some values outside the clamp range
+    grads = [torch.randn(n, generator=g) * (0.1 if k else 1.0) for k in range(4)]
+    grads[1][::7] = 0.0
+    lam_w = 5e3 * 4.0
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1.0)
+    p, gd = p0.clone().cuda(), torch.zeros(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for k, gk in enumerate(grads):
+        with torch.no_grad():
+            ref.copy_(ref.clamp(orc.CLAMP_LO, orc.CLAMP_HI))
+        opt.zero_grad()
+        (lam_w * torch.mean(ref ** 2)).backward()
+        ref.grad += gk
+        opt.step()
+        gd.copy_(gk.cuda() * 2.0)                        # pretend two ranks summed: grad_scale = 1/2
+        eng.adam_step(p, gd, m, v, 1.0, 0.9, 0.999, 1e-8, k + 1, reg_coef=2.0 * lam_w / n, grad_scale=0.5)
+        assert float(gd.abs().max()) == 0.0              # the kernel leaves the gradient buffer zeroed
+        # lr = 1: the first update is +-1 * sign(g); compare with an absolute tolerance on O(100) values
+        assert torch.allclose(p.cpu(), ref.detach(), rtol=0, atol=2e-4), k
+
+
+def test_texreg_value():
+    eng = _eng()
+    x = torch.rand(3, 64, 64) * 400 - 200
+    want = 7.0 * torch.mean(x.clamp(orc.CLAMP_LO, orc.CLAMP_HI) ** 2)
+    acc = torch.zeros(1, device="cuda")
+    eng.texreg_value(x.cuda(), 7.0 / x.numel(), acc)
+    assert abs(float(acc) - float(want)) <= 1e-5 * float(want)

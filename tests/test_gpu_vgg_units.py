@@ -1,0 +1,82 @@
+"""GPU parity of single VGG-side kernels through the unit C-ABI entry points, for BOTH implementations:
+SIMT (fp32 CUDA cores) and TC (tcgen05 tensor cores, bf16x3 split) — against torch fp32 CPU ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc")]
+
+
+def _eng():
+    from stylemesh_b200 import engine
+    return engine
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+CONV_SHAPES = [(64, 64, 24, 32), (64, 128, 17, 23), (128, 256, 12, 17), (256, 256, 9, 12), (512, 512, 6, 8),
+               (256, 512, 3, 4)]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("cin,cout,h,w", CONV_SHAPES)
+def test_conv3x3_bias_relu_forward(impl, cin, cout, h, w):
+    eng = _eng()
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(cin, h, w, generator=g) * 50
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.unsqueeze(0), wt, b, padding=1))[0]
+    out = eng.unit_conv3x3(impl, x.cuda(), wt, b, relu=True).cpu()
+    assert _rel(out, ref) < 5e-5, _rel(out, ref)
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("cin,cout,h,w", CONV_SHAPES)
+def test_conv3x3_data_gradient(impl, cin, cout, h, w):
+    eng = _eng()
+    g = torch.Generator().manual_seed(7 * cin + cout + w)
+    x = torch.randn(1, cin, h, w, generator=g).requires_grad_(True)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    dy = torch.randn(1, cout, h, w, generator=g)
+    F.conv2d(x, wt, None, padding=1).backward(dy)
+    out = eng.unit_conv3x3(impl, dy[0].cuda(), wt, None, relu=False, transpose_flip=True).cpu()
+    assert _rel(out, x.grad[0]) < 5e-5, _rel(out, x.grad[0])
+
+
+@pytest.mark.parametrize("h,w", [(24, 32), (17, 23), (2, 2), (5, 3)])
+def test_maxpool_forward_backward(h, w):
+    eng = _eng()
+    g = torch.Generator().manual_seed(h * w)
+    y = F.relu(torch.randn(1, 64, h, w, generator=g)).requires_grad_(True)     # post-ReLU (ties at 0 happen)
+    p = F.max_pool2d(y, 2, 2)
+    gp = torch.randn(p.shape, generator=g)
+    p.backward(gp)
+    out = eng.unit_maxpool(y.detach()[0].cuda()).cpu()
+    assert torch.allclose(out, p.detach()[0], rtol=1e-5, atol=1e-6)
+    # our backward also applies the ReLU mask of y (y > 0)
+    want = y.grad[0] * (y.detach()[0] > 0)
+    dx = eng.unit_maxpool_bwd(gp[0].cuda(), y.detach()[0].cuda()).cpu()
+    assert torch.allclose(dx, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("c,h,w,masked", [(64, 24, 32, False), (64, 48, 64, True), (128, 24, 32, True),
+                                          (256, 12, 16, False), (512, 6, 8, True), (512, 3, 4, False),
+                                          (256, 31, 37, True)])
+def test_masked_gram(impl, c, h, w, masked):
+    eng = _eng()
+    g = torch.Generator().manual_seed(c + h + w)
+    f = F.relu(torch.randn(c, h, w, generator=g)) * 30
+    mask = (torch.rand(h * w, generator=g) > 0.3).float() if masked else None
+    fm = f.reshape(c, -1) * (mask if masked else 1.0)
+    n = float(mask.sum()) if masked else float(h * w)
+    ref = fm.double() @ fm.double().t() / n
+    out = eng.unit_gram(impl, f.cuda(), None if mask is None else mask.cuda(), 1.0 / n).cpu()
+    assert _rel(out.double(), ref) < 2e-5, _rel(out.double(), ref)
+    assert torch.allclose(out, out.t(), rtol=1e-5, atol=1e-5 * float(out.abs().max()))     # symmetry property
