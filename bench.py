@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — texture-optimisation views/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" = one view per rank through the whole hot path: UV sample of the 2048^2 x 4-layer texture -> VGG conv1_1..
+conv5_1 -> Gram style + content losses (+ VGG of the content target, recomputed every step like the reference) ->
+backward -> UV scatter-add -> [one NCCL all-reduce of the texture gradient] -> fused Adam.  Inputs: synthetic
+640x480 UV views, He-init VGG weights, random-init texture.
+
+Legs (all in this process, one after another):
+  value      device-resident views, K steps, CUDA events, max over ranks            -> "value", "ms_per_step"
+  e2e        same step through the public module API from PINNED HOST buffers, H2D copy of the view and D2H read of
+             the loss inside the timed region                                        -> "e2e"
+  roofline   a few extra steps with per-kernel-class CUDA-event timing enabled       -> "roofline", "kernel_ms"
+  cpu        the CPU oracle (reference algorithm, torch fp32, all host threads) on a bounded sample of the same
+             workload, rank 0 at N=1 only                                            -> "cpu_baseline"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "texture-optim views/sec"
+UNIT = "views/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="only2D")
+    ap.add_argument("--texture", type=int, default=2048)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--view", default="480x640", help="HxW of the UV maps / rgb target")
+    ap.add_argument("--style", default="768x970", help="HxW of the synthetic style image (14-2.jpg is 768x970)")
+    ap.add_argument("--views-per-gpu", type=int, default=4)
+    ap.add_argument("--cache-content-targets", action="store_true",
+                    help="reuse VGG(target) per view (SURVEY §8f.1); OFF for the headline number")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "simt"])
+    return ap.parse_args()
+
+
+def workload_config(args):
+    vh, vw = [int(x) for x in args.view.split("x")]
+    return {
+        "workload": f"StyleMesh per-view texture optimisation: {args.texture}^2 x {args.layers}-layer texture, "
+                    f"{vw}x{vh} synthetic UV views, 5-layer Gram style + r42 content + tex_reg ('{args.preset}' flags), "
+                    f"VGG19 conv1_1..conv5_1, Adam lr=1",
+        "texture": args.texture, "hierarchical_layers": args.layers, "view_hw": [vh, vw], "preset": args.preset,
+        "views_per_gpu": args.views_per_gpu, "content_target_vgg": "cached" if args.cache_content_targets else
+        "recomputed every step (as the reference does)",
+        "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush needed",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# shared workload construction
+# ---------------------------------------------------------------------------------------------------------------
+def make_views(args, rank: int):
+    from stylemesh_b200 import synthetic as syn
+    vh, vw = [int(x) for x in args.view.split("x")]
+    preset = syn.PRESETS[args.preset]
+    sizes = syn.pyramid_sizes((vh, vw), preset["pyramid_levels"]) if preset["pyramid_levels"] > 1 else [(vh, vw)]
+    return [syn.make_view(1000 + rank * args.views_per_gpu + i, (vh, vw), sizes) for i in range(args.views_per_gpu)]
+
+
+def build_ours(args, device, tmpdir):
+    from stylemesh_b200 import synthetic as syn
+    from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline
+    if args.conv_impl:
+        os.environ["SMB_CONV_IMPL"] = args.conv_impl
+    preset = syn.PRESETS[args.preset]
+    sh, sw = [int(x) for x in args.style.split("x")]
+    vgg_path = os.path.join(tmpdir, "vgg_synth.pth")
+    torch.save(syn.make_vgg_state_dict(0, bias_scale=0.0), vgg_path)
+    torch.manual_seed(0)                                  # texture init = torch.rand like the reference
+    mdl = TextureOptimizationStyleTransferPipeline(
+        args.texture, args.texture, hierarchical_texture=True, hierarchical_layers=args.layers,
+        random_texture_init=True, style_image=syn.make_style_image(7, sh, sw),
+        style_weights=list(preset["style_weights"]), vgg_gatys_model_path=vgg_path,
+        use_angle_weight=preset["use_angle_weight"], use_depth_scaling=preset["use_depth_scaling"],
+        style_pyramid_mode=preset["style_pyramid_mode"], gram_mode=preset["gram_mode"],
+        angle_threshold=preset["angle_threshold"], learning_rate=1.0, decay_gamma=0.1, decay_step_size=3,
+        loss_weights=dict(preset["loss_weights"]), save_texture=False)
+    mdl.to(device)
+    mdl.vgg_loss.cache_content_targets = bool(args.cache_content_targets)
+    (opt,), _ = mdl.configure_optimizers()
+    return mdl, opt
+
+
+def one_step(mdl, opt, batch, i):
+    opt.zero_grad()
+    out = mdl.training_step(batch, i)
+    out["loss"].backward()
+    opt.step()
+    return out["loss"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from stylemesh_b200 import engine as eng
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device; there is no CPU path. Use --impl reference for the "
+                         "CPU baseline.")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=device)
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tmpdir = tempfile.mkdtemp(prefix="smb_bench_")
+    mdl, opt = build_ours(args, device, tmpdir)
+    host_views = make_views(args, rank)
+    dev_batches = [v.to(device).as_batch() for v in host_views]
+    nv = len(dev_batches)
+
+    # ------------------------------------------------ value leg (device-resident inputs) ----------------------
+    mdl.cache_view_plans = True                 # masks / counts of a resident view are inputs, built once
+    for i in range(max(args.warmup, 1)):        # includes the one-off style-target pass and all allocations
+        one_step(mdl, opt, dev_batches[i % nv], i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        one_step(mdl, opt, dev_batches[i % nv], args.warmup + i)
+    ev1.record()
+    barrier()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    value = world * args.steps / (total_ms / 1e3)
+
+    # ------------------------------------------------ e2e leg (host buffers through the public API) -----------
+    e2e = None
+    if not args.no_e2e:
+        mdl.cache_view_plans = False            # every step sees a fresh host batch: plan rebuilt, one host sync
+        pinned = [v.pin() for v in host_views]
+        h2d = pinned[0].h2d_bytes()
+        for i in range(2):
+            b = pinned[i % nv].to(device, non_blocking=True).as_batch()
+            float(one_step(mdl, opt, b, i))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            b = pinned[i % nv].to(device, non_blocking=True).as_batch()         # H2D of this step's view
+            loss = one_step(mdl, opt, b, i)
+            _ = mdl._loss_buf.to("cpu")                                         # D2H read of the step's 4 loss terms
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.steps / (float(ems) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 16, "ms_per_step": float(ems) / args.steps}
+
+    # ------------------------------------------------ roofline pass (per-kernel-class events) ------------------
+    roof, kernel_ms = None, None
+    if rank == 0:
+        mdl.cache_view_plans = True
+        vgg = mdl.vgg_loss.vgg.engine()
+        nsteps = min(5, max(2, args.steps))
+        vgg.set_timing(True)
+        for i in range(nsteps):
+            one_step(mdl, opt, dev_batches[i % nv], i)
+        t = vgg.read_timing()
+        vgg.set_timing(False)
+        kernel_ms = {k: round(v["ms"] / nsteps, 4) for k, v in t.items()}
+        conv_ms = (t["igemm_conv_fwd"]["ms"] + t["igemm_conv_dgrad"]["ms"]) / nsteps
+        conv_fl = (t["igemm_conv_fwd"]["flops"] + t["igemm_conv_dgrad"]["flops"]) / nsteps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roof = {"kernel": "igemm_tc_kernel (VGG conv forward + data-gradient launches)", "bound": "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms,
+                "executed_bf16_tflops": 3.0 * achieved,
+                "note": "achieved = fp32-equivalent algorithmic FLOPs (2*P*Cout*Cin*9 per launch); each is executed "
+                        "as 3 bf16 tcgen05 MMAs (hi*hi+lo*hi+hi*lo) for fp32-grade parity, so frac <= 1/3 by "
+                        "construction; executed_bf16_tflops/peak is the tensor-pipe fraction"}
+
+    # ------------------------------------------------ CPU baseline (oracle port) -------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_oracle(args, budget_s=args.cpu_budget_s, max_steps=8)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 (tensor-core convs/Gram as 3x bf16 split products, fp32 accumulate)", "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roof, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu,
+        "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "tc"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = None, warmup: int = 1):
+    from oracle import stylemesh_oracle as orc
+    from stylemesh_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    preset = syn.PRESETS[args.preset]
+    sh, sw = [int(x) for x in args.style.split("x")]
+    sd = syn.make_vgg_state_dict(0, bias_scale=0.0)
+    loss = orc.StyleContentOracle(vgg_params=sd, style_weights=list(preset["style_weights"]),
+                                  angle_threshold=preset["angle_threshold"],
+                                  style_pyramid_mode=preset["style_pyramid_mode"], gram_mode=preset["gram_mode"],
+                                  as_written=True)
+    loss.set_style_image(syn.make_style_image(7, sh, sw).unsqueeze(0))
+    torch.manual_seed(0)
+    layers = [torch.rand(3, args.texture // 2 ** i, args.texture // 2 ** i) for i in range(args.layers)]
+    cfg = orc.OracleConfig(use_angle_weight=preset["use_angle_weight"], use_depth_scaling=preset["use_depth_scaling"],
+                           loss_weights=dict(preset["loss_weights"]), hierarchical=True, learning_rate=1.0)
+    pipe = orc.OraclePipeline(layers, loss, cfg)
+    views = [v.as_batch() for v in make_views(args, 0)]
+    t0 = time.perf_counter()
+    for i in range(warmup):
+        pipe.step(views[i % len(views)])
+    t_first = (time.perf_counter() - t0) / max(warmup, 1)
+    n = fixed_steps if fixed_steps is not None else int(max(2, min(max_steps, budget_s / max(t_first, 1e-3))))
+    times = []
+    for i in range(n):
+        t = time.perf_counter()
+        pipe.step(views[i % len(views)])
+        times.append(time.perf_counter() - t)
+    med = statistics.median(times)
+    return {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full steps (median) of the same workload after {warmup} warm-up, torch {torch.__version__} "
+                      f"fp32 CPU, {cores} threads, reference-as-written (16-conv VGG on prediction and target)",
+            "seconds_per_step": med, "total_seconds": sum(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = run_cpu_oracle(args, budget_s=0, max_steps=0, fixed_steps=max(1, args.steps), warmup=max(1, args.warmup))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args), "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

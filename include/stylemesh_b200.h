@@ -124,6 +124,19 @@ int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target
  * Clears the pending gradients. */
 int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream);
 
+/* Number of kernel launches this library has issued in the process so far (bench.py: "gpu_launches"). */
+int64_t smb_launch_count(void);
+
+/* Per-kernel-class device timing with CUDA events on the launch stream (bench.py's roofline pass; adds two event
+ * records per launch, so it is off by default and never on during the headline timed region).
+ * Classes: 0 conv1_1 fwd, 1 igemm conv fwd, 2 igemm data-grad, 3 igemm Gram-backward, 4 Gram, 5 Gram-MSE,
+ *          6 pool fwd/bwd, 7 conv1_1 data-grad, 8 content MSE, 9 misc (mask / ReLU-split).
+ * smb_ctx_read_timing synchronises, returns accumulated milliseconds, algorithmic FLOPs (2*P*N*K*taps) and launch
+ * counts per class since the last read, and resets them.  Returns the number of classes (10). */
+#define SMB_NUM_TIMING_CLASSES 10
+int smb_ctx_set_timing(smb_ctx* ctx, int enabled);
+int smb_ctx_read_timing(smb_ctx* ctx, float* ms, double* flops, int* launches, int n);
+
 /* Bytes of device memory currently owned by the context. */
 int64_t smb_ctx_device_bytes(smb_ctx* ctx);
 

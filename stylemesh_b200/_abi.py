@@ -46,6 +46,9 @@ PROTOTYPES = [
     ("smb_level_style_term", _i, [_p, _i, _i, _p, _f, _p, _f, _p, _f, _p, _f, _p, _p, _p]),
     ("smb_level_content_term", _i, [_p, _i, _i, _p, _p, _f, _f, _p, _p]),
     ("smb_level_backward", _i, [_p, _i, _p, _p]),
+    ("smb_launch_count", _i64, []),
+    ("smb_ctx_set_timing", _i, [_p, _i]),
+    ("smb_ctx_read_timing", _i, [_p, _p, _p, _p, _i]),
     ("smb_ctx_device_bytes", _i64, [_p]),
     ("smb_unit_conv3x3", _i, [_i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     ("smb_unit_maxpool", _i, [_p, _i, _i, _i, _p, _p]),

@@ -2,6 +2,7 @@
 // working sets ("slots"), forward / loss-term / backward orchestration.  Every arithmetic step is one of the
 // kernels in texture_kernels.cu, vgg_simt_kernels.cu or tc_kernels.cu; nothing here computes on the CPU except
 // the one-time weight repacking.
+#include <atomic>
 #include <cstdarg>
 #include <memory>
 #include <mutex>
@@ -22,6 +23,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- VGG-19 topology up to conv5_1 (model/losses/content_and_style_losses.py:11-32,47-66) ---------------------
 static const int kCin[SMB_NUM_VGG_CONVS] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512};
@@ -92,11 +97,56 @@ struct Slot {
   }
 };
 
+// ---- optional per-kernel-class timing (CUDA events on the launch stream; used by bench.py's roofline pass) -------
+enum TimingClass : int {
+  CLS_CONV_FIRST = 0, CLS_IGEMM_FWD, CLS_IGEMM_DGRAD, CLS_IGEMM_GRAMBWD, CLS_GRAM, CLS_GRAM_MSE, CLS_POOL,
+  CLS_FIRST_DGRAD, CLS_CONTENT, CLS_MISC, CLS_COUNT
+};
+
+struct Timing {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cls; size_t e0, e1; };
+  std::vector<Rec> recs;
+  double flops[CLS_COUNT] = {0};
+  cudaEvent_t next() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  ~Timing() {
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+struct ScopedTimer {
+  Timing* t;
+  cudaStream_t st;
+  size_t e1 = 0;
+  ScopedTimer(Timing& tm, int cls, cudaStream_t s, double flops = 0.0) : t(tm.on ? &tm : nullptr), st(s) {
+    if (!t) return;
+    const size_t i0 = t->used;
+    cudaEventRecord(t->next(), st);
+    e1 = t->used;
+    t->next();
+    t->recs.push_back({cls, i0, e1});
+    t->flops[cls] += flops;
+  }
+  ~ScopedTimer() {
+    if (t) cudaEventRecord(t->pool[e1], st);
+  }
+};
+
 }  // namespace smb
 
 using namespace smb;
 
 struct smb_ctx {
+  Timing timing;
   int conv_impl = IMPL_TC, gram_impl = IMPL_TC;
   bool vgg_loaded = false;
   ConvLayer conv[SMB_NUM_VGG_CONVS];
@@ -151,6 +201,10 @@ static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, c
 static int gram(int impl, const Act& fm, float* partial, int nsplit, cudaStream_t st) {
   return impl == IMPL_TC ? launch_gram_tc(fm, partial, nsplit, st) : launch_gram_simt(fm, partial, nsplit, st);
 }
+static int igemm_timed(smb_ctx* ctx, int cls, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  ScopedTimer tm(ctx->timing, cls, st, 2.0 * (double)a.pixels() * b.N * b.K * b.taps);
+  return igemm(ctx->conv_impl, a, b, ep, st);
+}
 
 static Slot* get_slot(smb_ctx* ctx, int slot) {
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) {
@@ -199,14 +253,20 @@ static int gram_partials(smb_ctx* ctx, Slot& s, int conv, const float* rowmask, 
     fm.H = src.H;
     fm.W = src.W;
     fm.C = src.C;
-    rc = launch_mask_rows(src, rowmask, fm, st);
+    {
+      ScopedTimer tm(ctx->timing, CLS_MISC, st);
+      rc = launch_mask_rows(src, rowmask, fm, st);
+    }
     if (rc) return rc;
     src = fm;
   }
   const int ns = gram_num_splits(src.pixels(), src.C, ctx->gram_impl);
   rc = ensure_gram_partial(s, (int64_t)ns * src.C * src.C);
   if (rc) return rc;
-  rc = gram(ctx->gram_impl, src, s.gram_partial, ns, st);
+  {
+    ScopedTimer tm(ctx->timing, CLS_GRAM, st, 2.0 * (double)src.pixels() * src.C * src.C);
+    rc = gram(ctx->gram_impl, src, s.gram_partial, ns, st);
+  }
   if (rc) return rc;
   *used = src;
   *nsplit = ns;
@@ -386,12 +446,14 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
     ep.relu = 1;
     ep.out_hi = s.y[0].hi;
     ep.out_lo = s.y[0].lo;
+    ScopedTimer tm(ctx->timing, CLS_CONV_FIRST, st, 2.0 * 27 * 64 * (double)s.H * s.W);
     int rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
     if (rc) return rc;
   }
   for (int i = 1; i <= last_conv; ++i) {
     Act x = s.y[i - 1];
     if (kPoolBefore[i]) {
+      ScopedTimer tm(ctx->timing, CLS_POOL, st);
       int rc = launch_maxpool_fwd(s.y[i - 1], s.pooled[i], st);
       if (rc) return rc;
       x = s.pooled[i];
@@ -401,7 +463,7 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
     ep.relu = 1;
     ep.out_hi = s.y[i].hi;
     ep.out_lo = s.y[i].lo;
-    int rc = igemm(ctx->conv_impl, x, ctx->conv[i].fwd, ep, st);
+    int rc = igemm_timed(ctx, CLS_IGEMM_FWD, x, ctx->conv[i].fwd, ep, st);
     if (rc) return rc;
   }
   s.last_done = last_conv;
@@ -495,8 +557,11 @@ int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask,
   int ns = 0;
   int rc = gram_partials(ctx, s, conv, rowmask, &used, &ns, st);
   if (rc) return rc;
-  rc = launch_gram_mse(s.gram_partial, ns, used.C, inv_n, target0, coef0, target1, coef1, prev_sum,
-                       prev_sum ? avg_len : 1.f, gram_out, s.bmat_hi, s.bmat_lo, loss_accum, st);
+  {
+    ScopedTimer tm(ctx->timing, CLS_GRAM_MSE, st);
+    rc = launch_gram_mse(s.gram_partial, ns, used.C, inv_n, target0, coef0, target1, coef1, prev_sum,
+                         prev_sum ? avg_len : 1.f, gram_out, s.bmat_hi, s.bmat_lo, loss_accum, st);
+  }
   if (rc) return rc;
   if (inv_n == 0.f) return SMB_OK;   // empty mask: constant loss, zero gradient (cs:140-141)
   rc = ensure_pend(s, conv);
@@ -511,7 +576,7 @@ int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask,
   Epilogue ep;
   ep.out_f32 = s.pend[conv];
   if (s.has_pend[conv]) ep.addend = s.pend[conv];
-  rc = igemm(ctx->conv_impl, used, b, ep, st);
+  rc = igemm_timed(ctx, CLS_IGEMM_GRAMBWD, used, b, ep, st);
   if (rc) return rc;
   s.has_pend[conv] = true;
   return SMB_OK;
@@ -528,8 +593,11 @@ int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target
   if (rc) return rc;
   if (!s.has_pend[conv])
     SMB_CUDA_CHECK(cudaMemsetAsync(s.pend[conv], 0, s.y[conv].elems() * sizeof(float), (cudaStream_t)stream));
-  rc = launch_content_mse(s.y[conv], target_nhwc, rowmask, coef_loss, coef_grad, s.pend[conv], loss_accum,
-                          (cudaStream_t)stream);
+  {
+    ScopedTimer tm(ctx->timing, CLS_CONTENT, (cudaStream_t)stream);
+    rc = launch_content_mse(s.y[conv], target_nhwc, rowmask, coef_loss, coef_grad, s.pend[conv], loss_accum,
+                            (cudaStream_t)stream);
+  }
   if (rc) return rc;
   s.has_pend[conv] = true;
   return SMB_OK;
@@ -557,7 +625,11 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
       if (rc) return rc;
     }
   // top of the chain: dz = pend ⊙ (y > 0)
-  int rc = launch_relu_mask_split(s.pend[top], s.y[top], s.dz[top], st);
+  int rc;
+  {
+    ScopedTimer tm(ctx->timing, CLS_MISC, st);
+    rc = launch_relu_mask_split(s.pend[top], s.y[top], s.dz[top], st);
+  }
   if (rc) return rc;
   for (int i = top; i >= 1; --i) {
     const int j = i - 1;   // layer receiving the gradient
@@ -568,8 +640,9 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
       }
       Epilogue ep;
       ep.out_f32 = s.gpool[i];
-      rc = igemm(ctx->conv_impl, s.dz[i], ctx->conv[i].dgrad, ep, st);
+      rc = igemm_timed(ctx, CLS_IGEMM_DGRAD, s.dz[i], ctx->conv[i].dgrad, ep, st);
       if (rc) return rc;
+      ScopedTimer tm(ctx->timing, CLS_POOL, st);
       rc = launch_maxpool_bwd_relu(s.gpool[i], s.has_pend[j] ? s.pend[j] : nullptr, s.y[j], s.dz[j], st);
       if (rc) return rc;
     } else {
@@ -578,14 +651,51 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
       ep.sign_hi = s.y[j].hi;
       ep.out_hi = s.dz[j].hi;
       ep.out_lo = s.dz[j].lo;
-      rc = igemm(ctx->conv_impl, s.dz[i], ctx->conv[i].dgrad, ep, st);
+      rc = igemm_timed(ctx, CLS_IGEMM_DGRAD, s.dz[i], ctx->conv[i].dgrad, ep, st);
       if (rc) return rc;
     }
   }
-  rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
+  {
+    ScopedTimer tm(ctx->timing, CLS_FIRST_DGRAD, st, 2.0 * 27 * 64 * (double)s.H * s.W);
+    rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
+  }
   if (rc) return rc;
   for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;
   return SMB_OK;
+}
+
+int64_t smb_launch_count(void) { return (int64_t)smb::launch_count(); }
+
+int smb_ctx_set_timing(smb_ctx* ctx, int enabled) {
+  SMB_REQUIRE(ctx, "null context");
+  SMB_CUDA_CHECK(cudaDeviceSynchronize());
+  ctx->timing.on = enabled != 0;
+  ctx->timing.used = 0;
+  ctx->timing.recs.clear();
+  for (int i = 0; i < CLS_COUNT; ++i) ctx->timing.flops[i] = 0.0;
+  return SMB_OK;
+}
+
+int smb_ctx_read_timing(smb_ctx* ctx, float* ms, double* flops, int* launches, int n) {
+  SMB_REQUIRE(ctx && ms && flops && launches && n >= CLS_COUNT, "read_timing: need arrays of at least %d entries",
+              (int)CLS_COUNT);
+  SMB_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) {
+    ms[i] = 0.f;
+    flops[i] = 0.0;
+    launches[i] = 0;
+  }
+  for (const auto& r : ctx->timing.recs) {
+    float t = 0.f;
+    SMB_CUDA_CHECK(cudaEventElapsedTime(&t, ctx->timing.pool[r.e0], ctx->timing.pool[r.e1]));
+    ms[r.cls] += t;
+    launches[r.cls] += 1;
+  }
+  for (int i = 0; i < CLS_COUNT; ++i) flops[i] = ctx->timing.flops[i];
+  ctx->timing.used = 0;
+  ctx->timing.recs.clear();
+  for (int i = 0; i < CLS_COUNT; ++i) ctx->timing.flops[i] = 0.0;
+  return CLS_COUNT;
 }
 
 int64_t smb_ctx_device_bytes(smb_ctx* ctx) {

@@ -46,7 +46,15 @@ const char* get_error();
     }                                                                                     \
   } while (0)
 
-#define SMB_LAUNCH_CHECK() SMB_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of this library goes through SMB_LAUNCH_CHECK: it also feeds the launch counter that
+// bench.py reports as "gpu_launches"
+void count_launch();
+long long launch_count();
+#define SMB_LAUNCH_CHECK()                 \
+  do {                                     \
+    ::smb::count_launch();                 \
+    SMB_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

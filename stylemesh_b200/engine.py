@@ -107,6 +107,11 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, reg
     _abi.check(rc, "smb_adam_step")
 
 
+def launch_count() -> int:
+    """kernel launches issued by libstylemesh_b200.so in this process so far."""
+    return int(_abi.load().smb_launch_count())
+
+
 def texreg_value(param: torch.Tensor, coef: float, out_accum: torch.Tensor, clamp=(CLAMP_LO, CLAMP_HI)) -> None:
     lib = _abi.load()
     rc = lib.smb_texreg_value(_abi.ptr(param), param.numel(), coef, clamp[0], clamp[1], _abi.ptr(out_accum),
@@ -172,6 +177,20 @@ class VGGEngine:
 
     def device_bytes(self) -> int:
         return int(self._lib.smb_ctx_device_bytes(self._ctx))
+
+    # -- per-kernel-class timing (bench.py roofline pass) ------------------------------------------------------
+    TIMING_CLASSES = ["conv1_1_fwd", "igemm_conv_fwd", "igemm_conv_dgrad", "igemm_gram_bwd", "gram", "gram_mse",
+                      "pool", "conv1_1_dgrad", "content_mse", "misc"]
+
+    def set_timing(self, enabled: bool) -> None:
+        _abi.check(self._lib.smb_ctx_set_timing(self._ctx, int(bool(enabled))), "smb_ctx_set_timing")
+
+    def read_timing(self) -> Dict[str, dict]:
+        n = len(self.TIMING_CLASSES)
+        ms, fl, cnt = (C.c_float * n)(), (C.c_double * n)(), (C.c_int * n)()
+        _abi.check(self._lib.smb_ctx_read_timing(self._ctx, ms, fl, cnt, n), "smb_ctx_read_timing")
+        return {name: {"ms": float(ms[i]), "flops": float(fl[i]), "launches": int(cnt[i])}
+                for i, name in enumerate(self.TIMING_CLASSES)}
 
     # -- forward / features ---------------------------------------------------------------------------------
     def forward(self, slot: int, image: torch.Tensor, last_conv: int) -> None:

@@ -19,7 +19,7 @@ def _rel(a, b):
 
 
 CONV_SHAPES = [(64, 64, 24, 32), (64, 128, 17, 23), (128, 256, 12, 17), (256, 256, 9, 12), (512, 512, 6, 8),
-               (256, 512, 3, 4)]
+               (256, 512, 3, 4), (64, 256, 120, 160)]   # the last one selects the 256-wide N tile
 
 
 @pytest.mark.parametrize("impl", IMPLS)

@@ -1,12 +1,22 @@
 #!/bin/bash
-# First-contact GPU validation: every test file in its own process (a trap in one tcgen05 kernel must not hide the
-# other results), logs under gpurun_out/.  Usage (from the repo root on the GPU box): bash tools/gpu_check.sh
+# GPU validation driver: every group in its own process (a trap in one tcgen05 kernel must not hide the other
+# results), logs under gpurun_out/.  Usage (repo root on the GPU box): bash tools/gpu_check.sh [quick]
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in test_gpu_texture test_gpu_vgg_units test_gpu_pipeline; do
-  echo "=== $f"
-  timeout 900 python -m pytest tests/$f.py -q -m gpu -x --timeout 600 ${PYTEST_EXTRA} > gpurun_out/$f.log 2>&1
-  echo "exit $?" >> gpurun_out/$f.log
-  tail -n 25 gpurun_out/$f.log
-done
+python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/gpu.txt
+run() {  # name, pytest args...
+  local name=$1; shift
+  echo "=== $name"
+  timeout 900 python -m pytest "$@" -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  echo "exit $?" >> gpurun_out/$name.log
+  grep -E "passed|failed|error|exit" gpurun_out/$name.log | tail -n 4
+  grep -E "^(FAILED|ERROR)" gpurun_out/$name.log | head -n 30
+}
+run texture tests/test_gpu_texture.py
+run units_simt tests/test_gpu_vgg_units.py -k "simt or maxpool"
+run units_tc tests/test_gpu_vgg_units.py -k "tc"
+run pipeline_simt tests/test_gpu_pipeline.py -k "simt"
+run pipeline_tc tests/test_gpu_pipeline.py -k "not simt"
+echo "=== smoke"
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log; tail -n 3 gpurun_out/smoke.log
