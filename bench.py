@@ -233,7 +233,7 @@ def run_ours(args):
         h2d = pinned[0].h2d_bytes()
         for i in range(2):
             b = pinned[i % nv].to(device, non_blocking=True).as_batch()
-            float(one_step(mdl, opt, b, i))
+            float(one_step(mdl, opt, b, i).detach())
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -289,7 +289,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -298,7 +298,7 @@ def run_ours(args):
         "roofline": roof, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu,
         "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "tc"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
     }
-    print(json.dumps(line))
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -307,7 +307,8 @@ def run_ours(args):
 def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = None, warmup: int = 1):
     from oracle import stylemesh_oracle as orc
     from stylemesh_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
+    from stylemesh_b200.hostinfo import usable_cpus
+    cores = usable_cpus()                      # cgroup quota / affinity aware (os.cpu_count() over-reports)
     torch.set_num_threads(cores)
     preset = syn.PRESETS[args.preset]
     sh, sw = [int(x) for x in args.style.split("x")]
@@ -343,7 +344,7 @@ def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = Non
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     res = run_cpu_oracle(args, budget_s=0, max_steps=0, fixed_steps=max(1, args.steps), warmup=max(1, args.warmup))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
@@ -354,15 +355,20 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # exactly ONE JSON line on stdout: library / reference-style prints ("Use style image pyramid ...") go to stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout = real_stdout
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

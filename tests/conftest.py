@@ -10,7 +10,17 @@ for p in (REPO, os.path.join(REPO, "tests", "golden")):
         sys.path.insert(0, p)
 
 
+def _size_thread_pool():
+    try:
+        import torch
+        from stylemesh_b200.hostinfo import usable_cpus
+        torch.set_num_threads(usable_cpus())
+    except Exception:  # pragma: no cover
+        pass
+
+
 def pytest_configure(config):
+    _size_thread_pool()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

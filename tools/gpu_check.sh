@@ -8,7 +8,7 @@ python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/gpu.txt
 run() {  # name, pytest args...
   local name=$1; shift
   echo "=== $name"
-  timeout 900 python -m pytest "$@" -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  SMB_PARITY_LOG=gpurun_out/parity_stats.jsonl timeout 1200 python -m pytest "$@" -q -m gpu --timeout 900 -p no:cacheprovider > gpurun_out/$name.log 2>&1
   echo "exit $?" >> gpurun_out/$name.log
   grep -E "passed|failed|error|exit" gpurun_out/$name.log | tail -n 4
   grep -E "^(FAILED|ERROR)" gpurun_out/$name.log | head -n 30
