@@ -29,7 +29,8 @@ extern "C" {
 
 /* implementation selectors for smb_ctx_set_impl */
 #define SMB_IMPL_SIMT 0 /* fp32 CUDA-core cross-check kernels            */
-#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (default product) */
+#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (default product; convs: persistent stream-K kernel) */
+#define SMB_IMPL_TC_V1 2 /* convs only: first-generation tcgen05 kernel, one output tile per CTA             */
 
 typedef struct smb_ctx smb_ctx;
 

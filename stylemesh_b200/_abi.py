@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "lib", "libstylemesh_b200.so")
 NUM_VGG_CONVS = 13
 IMPL_SIMT = 0
 IMPL_TC = 1
+IMPL_TC_V1 = 2
 
 # (name, restype, argtypes) — must list every symbol of include/stylemesh_b200.h (checked by tests/test_abi.py)
 _f = C.c_float

@@ -196,7 +196,9 @@ static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& ou
 }
 
 static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  return impl == IMPL_TC ? launch_igemm_tc(a, b, ep, st) : launch_igemm_simt(a, b, ep, st);
+  if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
+  if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
+  return launch_igemm_simt(a, b, ep, st);
 }
 static int gram(int impl, const Act& fm, float* partial, int nsplit, cudaStream_t st) {
   return impl == IMPL_TC ? launch_gram_tc(fm, partial, nsplit, st) : launch_gram_simt(fm, partial, nsplit, st);
@@ -368,8 +370,9 @@ void smb_ctx_destroy(smb_ctx* ctx) { delete ctx; }
 
 int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl) {
   SMB_REQUIRE(ctx, "null context");
-  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC) && (gram_impl == IMPL_SIMT || gram_impl == IMPL_TC),
-              "impl must be SMB_IMPL_SIMT or SMB_IMPL_TC");
+  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC || conv_impl == IMPL_TC_V1) &&
+                  (gram_impl == IMPL_SIMT || gram_impl == IMPL_TC),
+              "conv_impl must be SMB_IMPL_SIMT / SMB_IMPL_TC / SMB_IMPL_TC_V1, gram_impl SMB_IMPL_SIMT / SMB_IMPL_TC");
   ctx->conv_impl = conv_impl;
   ctx->gram_impl = gram_impl;
   return SMB_OK;

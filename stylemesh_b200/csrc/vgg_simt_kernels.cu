@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
                                                                float* __restrict__ dimg) {
-  __shared__ float sw[9][COUT][3];   // [r*3+s][co][ci]
-  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i / 27, k = i % 27, ci = k / 9, rs = k % 9;
-    sw[rs][co][ci] = w_oihw[i];
+  __shared__ float4 sw[9][COUT];    // [r*3+s][co] = (w[co][0][r][s], w[co][1][r][s], w[co][2][r][s], 0)
+  for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) {
+    const int rs = i / COUT, co = i % COUT;
+    sw[rs][co] = make_float4(w_oihw[co * 27 + rs], w_oihw[co * 27 + 9 + rs], w_oihw[co * 27 + 18 + rs], 0.f);
   }
   __syncthreads();
   const int H = dz.H, W = dz.W;
@@ -176,10 +176,10 @@ __global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const flo
       for (int j = 0; j < 4; ++j) {
         const float v0 = bf16lo_to_f(hw[j]) + bf16lo_to_f(lw[j]);
         const float v1 = bf16hi_to_f(hw[j]) + bf16hi_to_f(lw[j]);
-        const float* w0 = sw[rs][c8 + 2 * j];
-        const float* w1 = sw[rs][c8 + 2 * j + 1];
-        a0 = fmaf(v0, w0[0], a0); a1 = fmaf(v0, w0[1], a1); a2 = fmaf(v0, w0[2], a2);
-        a0 = fmaf(v1, w1[0], a0); a1 = fmaf(v1, w1[1], a1); a2 = fmaf(v1, w1[2], a2);
+        const float4 w0 = sw[rs][c8 + 2 * j];
+        const float4 w1 = sw[rs][c8 + 2 * j + 1];
+        a0 = fmaf(v0, w0.x, a0); a1 = fmaf(v0, w0.y, a1); a2 = fmaf(v0, w0.z, a2);
+        a0 = fmaf(v1, w1.x, a0); a1 = fmaf(v1, w1.y, a1); a2 = fmaf(v1, w1.z, a2);
       }
     }
   }
@@ -450,14 +450,25 @@ __global__ void __launch_bounds__(256) gram_mse_kernel(const float* __restrict__
                                                        float* __restrict__ g_out, __nv_bfloat16* __restrict__ b_hi,
                                                        __nv_bfloat16* __restrict__ b_lo,
                                                        float* __restrict__ loss_out) {
+  // block = 32 consecutive Gram elements x 8 split groups: group sg sums partial[sg], partial[sg+8], ... (coalesced
+  // 128-byte rows), the groups are combined in a fixed order => deterministic, and no thread walks all splits alone
+  __shared__ float s_acc[8][33];
   const int64_t CC = (int64_t)C * C;
   const float inv_cc = 1.f / (float)CC;
   const float inv_len = 1.f / avg_len;
+  const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (e < CC)
+    for (int s = sg; s < nsplit; s += 8) acc += __ldg(partial + (int64_t)s * CC + e);
+  s_acc[sg][lane] = acc;
+  __syncthreads();
+  if (sg != 0) return;
   float lacc = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < CC; e += stride) {
+  if (e < CC) {
     float g = 0.f;
-    for (int s = 0; s < nsplit; ++s) g += __ldg(partial + (int64_t)s * CC + e);   // fixed order: deterministic
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g += s_acc[k][lane];
     g *= inv_n;
     if (g_out) g_out[e] = g;
     float ghat = g;
@@ -473,15 +484,15 @@ __global__ void __launch_bounds__(256) gram_mse_kernel(const float* __restrict__
       lacc = fmaf(coef1 * diff, diff, lacc);
       d = fmaf(coef1, diff, d);
     }
-    // dL/dGhat = 2 d / C^2 ; dL/dG_unnormalised-per-pixel-factor folded: (2 inv_n / len) * dGhat
+    // dL/dGhat = 2 d / C^2 ; gradient seed for dF = Fm * Bmat:  Bmat = (2 inv_n / len) * dL/dGhat
     const float bm = (2.f * inv_n * inv_len) * (2.f * d * inv_cc);
     __nv_bfloat16 h, l;
     split2(bm, h, l);
     b_hi[e] = h;
     b_lo[e] = l;
   }
-  lacc = block_sum(lacc);
-  if (threadIdx.x == 0) atomicAdd(loss_out, lacc * inv_cc);
+  lacc = warp_sum(lacc);
+  if (lane == 0) atomicAdd(loss_out, lacc * inv_cc);
 }
 
 // ============================================================================================================
@@ -629,8 +640,8 @@ int launch_gram_mse(const float* partial, int nsplit, int C, float inv_n, const 
                     __nv_bfloat16* b_hi, __nv_bfloat16* b_lo, float* loss_out, cudaStream_t st) {
   SMB_REQUIRE(y0 != nullptr && avg_len >= 1.f, "gram_mse: need a target and avg_len >= 1");
   const int64_t CC = (int64_t)C * C;
-  gram_mse_kernel<<<grid_for(CC, 256, 148 * 4), 256, 0, st>>>(partial, nsplit, C, inv_n, y0, coef0, y1, coef1,
-                                                               prev_sum, avg_len, g_out, b_hi, b_lo, loss_out);
+  gram_mse_kernel<<<(unsigned)ceil_div64(CC, 32), 256, 0, st>>>(partial, nsplit, C, inv_n, y0, coef0, y1, coef1,
+                                                                 prev_sum, avg_len, g_out, b_hi, b_lo, loss_out);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }

@@ -100,11 +100,14 @@ class LightningDataModule:
     def val_dataloader(self): return None
 
 
-def _to_device(obj: Any, device):
+def _to_device(obj: Any, device, _top: bool = True):
     if isinstance(obj, torch.Tensor):
         return obj.to(device, non_blocking=True)
     if isinstance(obj, (list, tuple)):
-        return type(obj)(_to_device(o, device) for o in obj)
+        moved = [_to_device(o, device, False) for o in obj]
+        if _top and len(obj) == 13 and isinstance(obj[8], torch.Tensor):
+            moved[8] = obj[8]          # the dataset index stays on the host: it keys the per-view plan cache
+        return type(obj)(moved)
     return obj
 
 
@@ -148,6 +151,8 @@ class Trainer:
         self._setup_distributed()
         model.to(device)
         model.trainer, model.logger = self, self.logger
+        if hasattr(model, "cache_view_plans"):
+            model.cache_view_plans = True      # views repeat (RepeatingSampler): build each view's mask plan once
         (optimizer,), schedulers = model.configure_optimizers()
         train_loader = datamodule.train_dataloader()
         val_loader = datamodule.val_dataloader()

@@ -6,7 +6,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc")]
+IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc"), pytest.param(2, id="tc1")]
+GRAM_IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc")]
 
 
 def _eng():
@@ -19,7 +20,8 @@ def _rel(a, b):
 
 
 CONV_SHAPES = [(64, 64, 24, 32), (64, 128, 17, 23), (128, 256, 12, 17), (256, 256, 9, 12), (512, 512, 6, 8),
-               (256, 512, 3, 4), (64, 256, 120, 160)]   # the last one selects the 256-wide N tile
+               (256, 512, 3, 4), (64, 256, 120, 160),   # 150 M-tiles x 256-wide N tile (v1: BN=256)
+               (512, 512, 30, 40), (256, 256, 60, 80), (128, 128, 33, 47)]   # stream-K: tiles split over many CTAs
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -65,7 +67,7 @@ def test_maxpool_forward_backward(h, w):
     assert torch.allclose(dx, want, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", GRAM_IMPLS)
 @pytest.mark.parametrize("c,h,w,masked", [(64, 24, 32, False), (64, 48, 64, True), (128, 24, 32, True),
                                           (256, 12, 16, False), (512, 6, 8, True), (512, 3, 4, False),
                                           (256, 31, 37, True)])
