@@ -1,10 +1,10 @@
 #!/bin/bash
 # GPU validation driver: every group in its own process (a trap in one tcgen05 kernel must not hide the other
-# results), logs under gpurun_out/.  Usage (repo root on the GPU box): bash tools/gpu_check.sh [quick]
+# results), logs under gpurun_out/.  Usage (repo root on the GPU box): bash tools/gpu_check.sh
 mkdir -p gpurun_out
+rm -f gpurun_out/parity_stats.jsonl
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/gpu.txt
 run() {  # name, pytest args...
   local name=$1; shift
   echo "=== $name"
@@ -15,7 +15,8 @@ run() {  # name, pytest args...
 }
 run texture tests/test_gpu_texture.py
 run units_simt tests/test_gpu_vgg_units.py -k "simt or maxpool"
-run units_tc tests/test_gpu_vgg_units.py -k "tc"
+run units_tc1 tests/test_gpu_vgg_units.py -k "tc1"
+run units_tc tests/test_gpu_vgg_units.py -k "tc and not tc1"
 run pipeline_simt tests/test_gpu_pipeline.py -k "simt"
 run pipeline_tc tests/test_gpu_pipeline.py -k "not simt"
 echo "=== smoke"
