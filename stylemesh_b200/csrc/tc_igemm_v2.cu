@@ -359,7 +359,10 @@ static int launch_igemm_tc2_bn(const Act& a, const PackedB& b, const Epilogue& e
   }
   // every CTA must be co-resident (owners wait for higher-indexed CTAs): 1 CTA/SM by shared memory, grid <= #SMs,
   // and the engine issues these launches on one stream with nothing else running on the device
-  const int grid = (int)std::min<long long>(num_sms, prm.total_units);
+  // small problems: do not shred a handful of tiles over all SMs (every extra split costs a 128 x BN fp32 partial
+  // write + read); keep at least ~16 K-iterations per CTA unless that would leave fewer CTAs than tiles
+  long long want = std::max<long long>(tiles, prm.total_units / 16);
+  const int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(num_sms, prm.total_units), want));
   igemm_tc2_kernel<BN><<<grid, I2_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
   SMB_LAUNCH_CHECK();
   return SMB_OK;

@@ -99,56 +99,59 @@ __global__ void __launch_bounds__(256) relu_mask_split_kernel(const float* __res
 }
 
 // ============================================================================================================
-// first layer: conv1_1 (3 -> Cout=64) straight from the fp32 planar image; one thread per pixel
+// first layer: conv1_1 (3 -> Cout=64) straight from the fp32 planar image.
+// Lane mapping: 8 lanes per pixel, each lane owns 8 consecutive output channels => every warp-wide 16-byte store
+// writes 4 complete 128-byte pixel rows (a thread-per-pixel mapping touches 32 different lines per instruction and
+// ran at 77 us per 640x480 launch; the activation write alone is 79 MB).
 // ============================================================================================================
 template <int COUT>
-__global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ img, int H, int W,
+__global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ img, int H, int W,
                                                              const float* __restrict__ w_oihw, Epilogue ep) {
-  __shared__ float sw[27][COUT];   // [ci*9 + r*3 + s][co]
+  static_assert(COUT == 64, "lane mapping assumes 8 lanes x 8 channels");
+  __shared__ __align__(16) float sw[27][COUT];   // [ci*9 + r*3 + s][co]
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i / 27, k = i % 27;   // w_oihw[co][ci][r][s] is contiguous in k = ci*9+r*3+s
+    const int co = i / 27, k = i % 27;           // w_oihw[co][ci][r][s] is contiguous in k = ci*9+r*3+s
     sw[k][co] = w_oihw[i];
   }
   __syncthreads();
   const int64_t P = (int64_t)H * W;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int y = (int)(p / W), x = (int)(p % W);
-  float in[27];
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int yy = y + r - 1, xx = x + s - 1;
-        in[ci * 9 + r * 3 + s] =
-            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (int64_t)ci * P + (int64_t)yy * W + xx) : 0.f;
-      }
+  const int lane = threadIdx.x & 31, chunk = lane & 7, sub = lane >> 3;
+  const int64_t warp_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
 #pragma unroll 1
-  for (int c0 = 0; c0 < COUT; c0 += 16) {
-    float acc[16];
+  for (int pass = 0; pass < 8; ++pass) {
+    const int64_t p = warp_base + pass * 4 + sub;
+    if (p >= P) continue;
+    const int y = (int)(p / W), x = (int)(p % W);
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
+    for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(&sw[k][c0 + j]);
-        acc[j] = fmaf(in[k], wv.x, acc[j]);
-        acc[j + 1] = fmaf(in[k], wv.y, acc[j + 1]);
-        acc[j + 2] = fmaf(in[k], wv.z, acc[j + 2]);
-        acc[j + 3] = fmaf(in[k], wv.w, acc[j + 3]);
-      }
-    }
-    epilogue_store<16>(ep, p, c0, COUT, acc);
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int yy = y + r - 1, xx = x + s2 - 1;
+          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (int64_t)ci * P + (int64_t)yy * W + xx)
+                                                                   : 0.f;
+          const int k = ci * 9 + r * 3 + s2;
+          const float4 w0 = *reinterpret_cast<const float4*>(&sw[k][chunk * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sw[k][chunk * 8 + 4]);
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+    epilogue_store<8>(ep, p, chunk * 8, COUT, acc);
   }
 }
 
 // data gradient of the first layer: dimg[ci][p] = sum_{r,s,co} dz(y-(r-1), x-(s-1))[co] * w[co][ci][r][s]
+// same 8-lanes-per-pixel mapping: every warp-wide 16-byte load reads 4 complete pixel rows of dz.
 template <int COUT>
-__global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
+__global__ void __launch_bounds__(256) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
                                                                float* __restrict__ dimg) {
+  static_assert(COUT == 64, "lane mapping assumes 8 lanes x 8 channels");
   __shared__ float4 sw[9][COUT];    // [r*3+s][co] = (w[co][0][r][s], w[co][1][r][s], w[co][2][r][s], 0)
   for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) {
     const int rs = i / COUT, co = i % COUT;
@@ -157,35 +160,46 @@ __global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const flo
   __syncthreads();
   const int H = dz.H, W = dz.W;
   const int64_t P = (int64_t)H * W;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int y = (int)(p / W), x = (int)(p % W);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const int lane = threadIdx.x & 31, chunk = lane & 7, sub = lane >> 3;
+  const int64_t warp_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
 #pragma unroll 1
-  for (int rs = 0; rs < 9; ++rs) {
-    const int r = rs / 3, s = rs % 3;
-    const int yy = y - (r - 1), xx = x - (s - 1);
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const int64_t q = ((int64_t)yy * W + xx) * COUT;
-#pragma unroll 2
-    for (int c8 = 0; c8 < COUT; c8 += 8) {
-      const uint4 h = __ldg(reinterpret_cast<const uint4*>(dz.hi + q + c8));
-      const uint4 l = __ldg(reinterpret_cast<const uint4*>(dz.lo + q + c8));
-      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  for (int pass = 0; pass < 8; ++pass) {
+    const int64_t p = warp_base + pass * 4 + sub;          // uniform over the 8 lanes of a pixel
+    const bool live = p < P;
+    const int y = live ? (int)(p / W) : 0, x = live ? (int)(p % W) : 0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v0 = bf16lo_to_f(hw[j]) + bf16lo_to_f(lw[j]);
-        const float v1 = bf16hi_to_f(hw[j]) + bf16hi_to_f(lw[j]);
-        const float4 w0 = sw[rs][c8 + 2 * j];
-        const float4 w1 = sw[rs][c8 + 2 * j + 1];
-        a0 = fmaf(v0, w0.x, a0); a1 = fmaf(v0, w0.y, a1); a2 = fmaf(v0, w0.z, a2);
-        a0 = fmaf(v1, w1.x, a0); a1 = fmaf(v1, w1.y, a1); a2 = fmaf(v1, w1.z, a2);
+    for (int rs = 0; rs < 9; ++rs) {
+      const int yy = y - (rs / 3 - 1), xx = x - (rs % 3 - 1);
+      if (live && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const int64_t q = ((int64_t)yy * W + xx) * COUT + chunk * 8;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(dz.hi + q));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(dz.lo + q));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = bf16lo_to_f(hw[j]) + bf16lo_to_f(lw[j]);
+          const float v1 = bf16hi_to_f(hw[j]) + bf16hi_to_f(lw[j]);
+          const float4 w0 = sw[rs][chunk * 8 + 2 * j];
+          const float4 w1 = sw[rs][chunk * 8 + 2 * j + 1];
+          a0 = fmaf(v0, w0.x, a0); a1 = fmaf(v0, w0.y, a1); a2 = fmaf(v0, w0.z, a2);
+          a0 = fmaf(v1, w1.x, a0); a1 = fmaf(v1, w1.y, a1); a2 = fmaf(v1, w1.z, a2);
+        }
       }
     }
+    // reduce over the 8 channel chunks of this pixel (lanes sub*8 .. sub*8+7)
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (live && chunk == 0) {
+      dimg[p] = a0;
+      dimg[P + p] = a1;
+      dimg[2 * P + p] = a2;
+    }
   }
-  dimg[p] = a0;
-  dimg[P + p] = a1;
-  dimg[2 * P + p] = a2;
 }
 
 // ============================================================================================================
@@ -239,61 +253,80 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(Act in, Act out) {
   *reinterpret_cast<uint4*>(out.lo + po * out.C + g * 8) = l;
 }
 
-// one thread per (input pixel, 8-channel group)
+// one thread per (2x2 window, 8-channel group): reads the four y pixels once, writes the four dz pixels.
+// Windows hanging over an odd trailing row/column carry no pooled gradient (floor mode) but their pixels still get
+// dz = addend masked by ReLU (or zero).
 __global__ void __launch_bounds__(256) maxpool_bwd_relu_kernel(const float* __restrict__ gp,
                                                                const float* __restrict__ addend, Act y, Act dz) {
   const int groups = y.C >> 3;
-  const int64_t total = y.pixels() * groups;
+  const int Ho = y.H >> 1, Wo = y.W >> 1;
+  const int Hc = (y.H + 1) >> 1, Wc = (y.W + 1) >> 1;
+  const int64_t total = (int64_t)Hc * Wc * groups;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = (int)(idx % groups);
-  const int64_t p = idx / groups;
-  const int yy = (int)(p / y.W), xx = (int)(p % y.W);
-  const int Ho = y.H >> 1, Wo = y.W >> 1;
-  const int yo = yy >> 1, xo = xx >> 1;
-  float out[8];
+  const int64_t wq = idx / groups;
+  const int wy = (int)(wq / Wc), wx = (int)(wq % Wc);
+  const bool pooled = (wy < Ho) && (wx < Wo);
+  float v[4][8];
+  bool exists[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) out[j] = 0.f;
-  if (addend) {   // pending loss gradient on a pre-pool layer: (pool-routed + addend) ⊙ (y > 0)
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(addend + p * y.C + g * 8));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(addend + p * y.C + g * 8 + 4));
-    out[0] = a0.x; out[1] = a0.y; out[2] = a0.z; out[3] = a0.w;
-    out[4] = a1.x; out[5] = a1.y; out[6] = a1.z; out[7] = a1.w;
+  for (int k = 0; k < 4; ++k) {
+    const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+    exists[k] = (yy < y.H) && (xx < y.W);
+    if (exists[k]) {
+      uint4 h, l;
+      load8(y, ((int64_t)yy * y.W + xx) * y.C + g * 8, v[k], h, l);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] = -1.f;
+    }
   }
-  if (yo < Ho && xo < Wo) {
-    const int me = ((yy & 1) << 1) | (xx & 1);
-    float v[4][8];
-    uint4 h, l;
+  float gv[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      load8(y, ((int64_t)(2 * yo + (k >> 1)) * y.W + (2 * xo + (k & 1))) * y.C + g * 8, v[k], h, l);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + ((int64_t)yo * Wo + xo) * y.C + g * 8));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + ((int64_t)yo * Wo + xo) * y.C + g * 8 + 4));
-    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+  if (pooled) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + ((int64_t)wy * Wo + wx) * y.C + g * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + ((int64_t)wy * Wo + wx) * y.C + g * 8 + 4));
+    gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w;
+    gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+  }
+  int arg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    arg[j] = 0;
+    float best = v[0][j];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (v[k][j] > best) { best = v[k][j]; arg[j] = k; }      // first maximum in window scan order wins
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!exists[k]) continue;
+    const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+    const int64_t off = ((int64_t)yy * y.W + xx) * y.C + g * 8;
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = 0.f;
+    if (addend) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addend + off));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(addend + off + 4));
+      out[0] = a0.x; out[1] = a0.y; out[2] = a0.z; out[3] = a0.w;
+      out[4] = a1.x; out[5] = a1.y; out[6] = a1.z; out[7] = a1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int arg = 0;
-      float best = v[0][j];
-#pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (v[k][j] > best) { best = v[k][j]; arg = k; }
-      const float val = out[j] + ((arg == me) ? gv[j] : 0.f);
-      out[j] = (v[me][j] > 0.f) ? val : 0.f;
+      const float val = out[j] + ((pooled && arg[j] == k) ? gv[j] : 0.f);
+      out[j] = (v[k][j] > 0.f) ? val : 0.f;
     }
-  } else if (addend) {   // odd trailing row/column: only the addend, still ReLU-masked
-    float v[8];
     uint4 h, l;
-    load8(y, p * y.C + g * 8, v, h, l);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = (v[j] > 0.f) ? out[j] : 0.f;
+    split2_pack(out[0], out[1], h.x, l.x);
+    split2_pack(out[2], out[3], h.y, l.y);
+    split2_pack(out[4], out[5], h.z, l.z);
+    split2_pack(out[6], out[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(dz.hi + off) = h;
+    *reinterpret_cast<uint4*>(dz.lo + off) = l;
   }
-  uint4 h, l;
-  split2_pack(out[0], out[1], h.x, l.x);
-  split2_pack(out[2], out[3], h.y, l.y);
-  split2_pack(out[4], out[5], h.z, l.z);
-  split2_pack(out[6], out[7], h.w, l.w);
-  *reinterpret_cast<uint4*>(dz.hi + p * y.C + g * 8) = h;
-  *reinterpret_cast<uint4*>(dz.lo + p * y.C + g * 8) = l;
 }
 
 // ============================================================================================================
@@ -573,7 +606,7 @@ int launch_conv_first_fwd(const float* img, int H, int W, const float* w_oihw, c
   ep.bias = bias;
   const int64_t P = (int64_t)H * W;
   if (P == 0) return SMB_OK;
-  conv_first_fwd_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(img, H, W, w_oihw, ep);
+  conv_first_fwd_kernel<64><<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(img, H, W, w_oihw, ep);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }
@@ -581,7 +614,7 @@ int launch_conv_first_dgrad(const Act& dz, const float* w_oihw, int Cout, float*
   SMB_REQUIRE(Cout == 64 && dz.C == 64, "conv_first_dgrad: only Cout=64 is built");
   const int64_t P = dz.pixels();
   if (P == 0) return SMB_OK;
-  conv_first_dgrad_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(dz, w_oihw, dimg);
+  conv_first_dgrad_kernel<64><<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(dz, w_oihw, dimg);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }
@@ -597,7 +630,7 @@ int launch_maxpool_fwd(const Act& in, const Act& out, cudaStream_t st) {
 int launch_maxpool_bwd_relu(const float* g_pooled, const float* addend, const Act& y, const Act& dz,
                             cudaStream_t st) {
   SMB_REQUIRE(y.C % 8 == 0 && dz.C == y.C && dz.H == y.H && dz.W == y.W, "maxpool_bwd: bad shapes");
-  const int64_t work = y.pixels() * (y.C >> 3);
+  const int64_t work = (int64_t)((y.H + 1) / 2) * ((y.W + 1) / 2) * (y.C >> 3);
   if (work == 0) return SMB_OK;
   maxpool_bwd_relu_kernel<<<(unsigned)ceil_div64(work, 256), 256, 0, st>>>(g_pooled, addend, y, dz);
   SMB_LAUNCH_CHECK();
