@@ -101,3 +101,18 @@ def test_cli_parser_accepts_reference_script_flags():
     assert a.texture_size == [4096, 4096] and a.style_weights == [1000.0, 1000.0, 10.0, 10.0, 1000.0]
     assert a.loss_weights == [["content", "7e1"], ["style", "1e-4"], ["tex_reg", "5e3"]]
     assert a.max_epochs == 7 and a.gpus == 1 and a.style_pyramid_mode == "multi"
+
+
+def test_reference_entry_point_shim_resolves_to_b200_modules():
+    """`python -m model.optimize` / `from model.model import ...` (what the reference scripts call) must resolve to
+    the B200 implementation."""
+    import importlib
+    import sys
+    for name in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
+        del sys.modules[name]
+    m = importlib.import_module("model.model")
+    o = importlib.import_module("model.optimize")
+    c = importlib.import_module("model.losses.content_and_style_losses")
+    assert m.TextureOptimizationStyleTransferPipeline.__module__ == "stylemesh_b200.model.model"
+    assert c.ContentAndStyleLoss.__module__ == "stylemesh_b200.model.losses.content_and_style_losses"
+    assert callable(o.main)
