@@ -99,59 +99,56 @@ __global__ void __launch_bounds__(256) relu_mask_split_kernel(const float* __res
 }
 
 // ============================================================================================================
-// first layer: conv1_1 (3 -> Cout=64) straight from the fp32 planar image.
-// Lane mapping: 8 lanes per pixel, each lane owns 8 consecutive output channels => every warp-wide 16-byte store
-// writes 4 complete 128-byte pixel rows (a thread-per-pixel mapping touches 32 different lines per instruction and
-// ran at 77 us per 640x480 launch; the activation write alone is 79 MB).
+// first layer: conv1_1 (3 -> Cout=64) straight from the fp32 planar image; one thread per pixel
 // ============================================================================================================
 template <int COUT>
-__global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ img, int H, int W,
+__global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ img, int H, int W,
                                                              const float* __restrict__ w_oihw, Epilogue ep) {
-  static_assert(COUT == 64, "lane mapping assumes 8 lanes x 8 channels");
-  __shared__ __align__(16) float sw[27][COUT];   // [ci*9 + r*3 + s][co]
+  __shared__ float sw[27][COUT];   // [ci*9 + r*3 + s][co]
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i / 27, k = i % 27;           // w_oihw[co][ci][r][s] is contiguous in k = ci*9+r*3+s
+    const int co = i / 27, k = i % 27;   // w_oihw[co][ci][r][s] is contiguous in k = ci*9+r*3+s
     sw[k][co] = w_oihw[i];
   }
   __syncthreads();
   const int64_t P = (int64_t)H * W;
-  const int lane = threadIdx.x & 31, chunk = lane & 7, sub = lane >> 3;
-  const int64_t warp_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        in[ci * 9 + r * 3 + s] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (int64_t)ci * P + (int64_t)yy * W + xx) : 0.f;
+      }
 #pragma unroll 1
-  for (int pass = 0; pass < 8; ++pass) {
-    const int64_t p = warp_base + pass * 4 + sub;
-    if (p >= P) continue;
-    const int y = (int)(p / W), x = (int)(p % W);
-    float acc[8];
+  for (int c0 = 0; c0 < COUT; c0 += 16) {
+    float acc[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+    for (int k = 0; k < 27; ++k) {
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) {
-          const int yy = y + r - 1, xx = x + s2 - 1;
-          const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + (int64_t)ci * P + (int64_t)yy * W + xx)
-                                                                   : 0.f;
-          const int k = ci * 9 + r * 3 + s2;
-          const float4 w0 = *reinterpret_cast<const float4*>(&sw[k][chunk * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&sw[k][chunk * 8 + 4]);
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
-        }
-    epilogue_store<8>(ep, p, chunk * 8, COUT, acc);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&sw[k][c0 + j]);
+        acc[j] = fmaf(in[k], wv.x, acc[j]);
+        acc[j + 1] = fmaf(in[k], wv.y, acc[j + 1]);
+        acc[j + 2] = fmaf(in[k], wv.z, acc[j + 2]);
+        acc[j + 3] = fmaf(in[k], wv.w, acc[j + 3]);
+      }
+    }
+    epilogue_store<16>(ep, p, c0, COUT, acc);
   }
 }
 
 // data gradient of the first layer: dimg[ci][p] = sum_{r,s,co} dz(y-(r-1), x-(s-1))[co] * w[co][ci][r][s]
-// same 8-lanes-per-pixel mapping: every warp-wide 16-byte load reads 4 complete pixel rows of dz.
 template <int COUT>
-__global__ void __launch_bounds__(256) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
+__global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
                                                                float* __restrict__ dimg) {
-  static_assert(COUT == 64, "lane mapping assumes 8 lanes x 8 channels");
   __shared__ float4 sw[9][COUT];    // [r*3+s][co] = (w[co][0][r][s], w[co][1][r][s], w[co][2][r][s], 0)
   for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) {
     const int rs = i / COUT, co = i % COUT;
@@ -160,46 +157,35 @@ __global__ void __launch_bounds__(256) conv_first_dgrad_kernel(Act dz, const flo
   __syncthreads();
   const int H = dz.H, W = dz.W;
   const int64_t P = (int64_t)H * W;
-  const int lane = threadIdx.x & 31, chunk = lane & 7, sub = lane >> 3;
-  const int64_t warp_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
-  for (int pass = 0; pass < 8; ++pass) {
-    const int64_t p = warp_base + pass * 4 + sub;          // uniform over the 8 lanes of a pixel
-    const bool live = p < P;
-    const int y = live ? (int)(p / W) : 0, x = live ? (int)(p % W) : 0;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int rs = 0; rs < 9; ++rs) {
+    const int r = rs / 3, s = rs % 3;
+    const int yy = y - (r - 1), xx = x - (s - 1);
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const int64_t q = ((int64_t)yy * W + xx) * COUT;
+#pragma unroll 2
+    for (int c8 = 0; c8 < COUT; c8 += 8) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(dz.hi + q + c8));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(dz.lo + q + c8));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int rs = 0; rs < 9; ++rs) {
-      const int yy = y - (rs / 3 - 1), xx = x - (rs % 3 - 1);
-      if (live && yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const int64_t q = ((int64_t)yy * W + xx) * COUT + chunk * 8;
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(dz.hi + q));
-        const uint4 l = __ldg(reinterpret_cast<const uint4*>(dz.lo + q));
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v0 = bf16lo_to_f(hw[j]) + bf16lo_to_f(lw[j]);
-          const float v1 = bf16hi_to_f(hw[j]) + bf16hi_to_f(lw[j]);
-          const float4 w0 = sw[rs][chunk * 8 + 2 * j];
-          const float4 w1 = sw[rs][chunk * 8 + 2 * j + 1];
-          a0 = fmaf(v0, w0.x, a0); a1 = fmaf(v0, w0.y, a1); a2 = fmaf(v0, w0.z, a2);
-          a0 = fmaf(v1, w1.x, a0); a1 = fmaf(v1, w1.y, a1); a2 = fmaf(v1, w1.z, a2);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = bf16lo_to_f(hw[j]) + bf16lo_to_f(lw[j]);
+        const float v1 = bf16hi_to_f(hw[j]) + bf16hi_to_f(lw[j]);
+        const float4 w0 = sw[rs][c8 + 2 * j];
+        const float4 w1 = sw[rs][c8 + 2 * j + 1];
+        a0 = fmaf(v0, w0.x, a0); a1 = fmaf(v0, w0.y, a1); a2 = fmaf(v0, w0.z, a2);
+        a0 = fmaf(v1, w1.x, a0); a1 = fmaf(v1, w1.y, a1); a2 = fmaf(v1, w1.z, a2);
       }
     }
-    // reduce over the 8 channel chunks of this pixel (lanes sub*8 .. sub*8+7)
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (live && chunk == 0) {
-      dimg[p] = a0;
-      dimg[P + p] = a1;
-      dimg[2 * P + p] = a2;
-    }
   }
+  dimg[p] = a0;
+  dimg[P + p] = a1;
+  dimg[2 * P + p] = a2;
 }
 
 // ============================================================================================================
@@ -606,7 +592,7 @@ int launch_conv_first_fwd(const float* img, int H, int W, const float* w_oihw, c
   ep.bias = bias;
   const int64_t P = (int64_t)H * W;
   if (P == 0) return SMB_OK;
-  conv_first_fwd_kernel<64><<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(img, H, W, w_oihw, ep);
+  conv_first_fwd_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(img, H, W, w_oihw, ep);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }
@@ -614,7 +600,7 @@ int launch_conv_first_dgrad(const Act& dz, const float* w_oihw, int Cout, float*
   SMB_REQUIRE(Cout == 64 && dz.C == 64, "conv_first_dgrad: only Cout=64 is built");
   const int64_t P = dz.pixels();
   if (P == 0) return SMB_OK;
-  conv_first_dgrad_kernel<64><<<(unsigned)ceil_div64(P, 256), 256, 0, st>>>(dz, w_oihw, dimg);
+  conv_first_dgrad_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(dz, w_oihw, dimg);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }
