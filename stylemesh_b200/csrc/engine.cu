@@ -196,6 +196,7 @@ static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& ou
 }
 
 static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  if (impl == IMPL_TC_PAIR) return (b.N % 256 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
   return launch_igemm_simt(a, b, ep, st);
@@ -370,7 +371,7 @@ void smb_ctx_destroy(smb_ctx* ctx) { delete ctx; }
 
 int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl) {
   SMB_REQUIRE(ctx, "null context");
-  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC || conv_impl == IMPL_TC_V1) &&
+  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC || conv_impl == IMPL_TC_V1 || conv_impl == IMPL_TC_PAIR) &&
                   (gram_impl == IMPL_SIMT || gram_impl == IMPL_TC),
               "conv_impl must be SMB_IMPL_SIMT / SMB_IMPL_TC / SMB_IMPL_TC_V1, gram_impl SMB_IMPL_SIMT / SMB_IMPL_TC");
   ctx->conv_impl = conv_impl;

@@ -301,6 +301,18 @@ static int ensure_workspace() {
   return SMB_OK;
 }
 
+// shared with the CTA-pair variant (tc_igemm_v3.cu): one workspace / epoch counter per process
+int igemm_streamk_workspace(float** ws, unsigned int** flags, unsigned int* epoch) {
+  int rc = ensure_workspace();
+  if (rc) return rc;
+  *ws = g_sk.ws;
+  *flags = g_sk.flags;
+  unsigned int e = ++g_sk.epoch;
+  if (e == 0) e = ++g_sk.epoch;
+  *epoch = e;
+  return SMB_OK;
+}
+
 template <int BN>
 static int launch_igemm_tc2_bn(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
   using Cfg = I2Cfg<BN>;

@@ -57,7 +57,8 @@ def assert_texels(got, want, what=""):
 
 
 def make_pipeline(spec, tmp_path, impl):
-    os.environ["SMB_CONV_IMPL"] = impl
+    # SMB_TEST_TC_VARIANT=pair|tc1 re-runs the "tc" cases on another tcgen05 conv kernel generation
+    os.environ["SMB_CONV_IMPL"] = os.environ.get("SMB_TEST_TC_VARIANT", "tc") if impl == "tc" else impl
     os.environ["SMB_GRAM_IMPL"] = impl
     from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline
     preset, sd, layers, view, style, hierarchical = build_inputs(spec)

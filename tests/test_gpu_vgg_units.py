@@ -6,7 +6,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc"), pytest.param(2, id="tc1")]
+IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc"), pytest.param(2, id="tc1"), pytest.param(3, id="pair")]
 GRAM_IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc")]
 
 
