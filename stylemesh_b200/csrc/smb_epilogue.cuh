@@ -101,31 +101,4 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, int64_t p, in
   }
 }
 
-// Warp-cooperative variant for the tcgen05 epilogues.  After tcgen05.ld each lane holds 32 consecutive channels of
-// ONE pixel row: storing that directly makes every 16-byte access of a warp hit 32 different 128-byte lines (LSU
-// wavefronts x32; measured: the data-gradient epilogues with addend + sign reads were as long as the MMA main loop of
-// the 64-channel layers).  Transposing the 32x32 block through a padded shared-memory tile lets 4 lanes cover one
-// row (8 channels each): 8 lines per access instead of 32, for loads (bias/addend/sign) and stores alike.
-// row_pixel(r) maps the warp-local row r (0..31) to its pixel index or -1 when the row is outside the image.
-constexpr int EPI_STAGE_FLOATS = 32 * 33;
-
-template <class RowPixel>
-__device__ __forceinline__ void epilogue_store_warp32(const Epilogue& ep, float* stage /* [32][33] of this warp */,
-                                                      int lane, RowPixel row_pixel, int n, int N, float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
-  __syncwarp();
-  const int cc = (lane & 3) * 8;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = 8 * i + (lane >> 2);
-    float t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = stage[rr * 33 + cc + j];
-    const int64_t p = row_pixel(rr);
-    if (p >= 0) epilogue_store<8>(ep, p, n + cc, N, t);
-  }
-  __syncwarp();
-}
-
 }  // namespace smb

@@ -26,7 +26,7 @@ constexpr int I2_BM = 128;
 constexpr int I2_BK = 64;
 constexpr int I2_A_BYTES = I2_BM * I2_BK * 2;
 constexpr int I2_SMEM_BUDGET = 196608;
-constexpr int I2_SMEM_EXTRA = 1024 + 256 + 4 * EPI_STAGE_FLOATS * 4;   // + epilogue transpose tiles
+constexpr int I2_SMEM_EXTRA = 1024 + 256;
 constexpr int I2_MAX_GRID = 148;
 
 struct IGemm2Params {
@@ -75,7 +75,6 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;      // [NBUF]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // 4 x [32][33]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ipt = prm.ipt;
@@ -239,13 +238,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
         if (owner) {
-          const int rbase = q * 32;
-          auto row_pixel = [&](int rr) -> int64_t {
-            const int r2 = rbase + rr;
-            const int y2 = y0 + r2 / prm.TW, x2 = x0 + r2 % prm.TW;
-            return (y2 < prm.H && x2 < prm.W) ? (int64_t)y2 * prm.W + x2 : (int64_t)-1;
-          };
-          epilogue_store_warp32(prm.ep, epi_stage + q * EPI_STAGE_FLOATS, lane, row_pixel, n0 + c, prm.N, v);
+          if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
         } else {
           float4* dst = reinterpret_cast<float4*>(my_slot + (size_t)row * BN + c);
 #pragma unroll

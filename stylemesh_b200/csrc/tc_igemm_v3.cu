@@ -25,7 +25,7 @@ constexpr int I3_A_BYTES = I3_BM * I3_BK * 2;           // 16 KiB per plane
 constexpr int I3_B_BYTES = (I3_BN / 2) * I3_BK * 2;     // 16 KiB per plane (this CTA's half of B)
 constexpr int I3_STAGE_BYTES = 2 * I3_A_BYTES + 2 * I3_B_BYTES;   // 64 KiB
 constexpr int I3_STAGES = 3;
-constexpr int I3_SMEM_EXTRA = 1024 + 256 + 4 * EPI_STAGE_FLOATS * 4;   // + epilogue transpose tiles
+constexpr int I3_SMEM_EXTRA = 1024 + 256;
 constexpr int I3_TMEM_COLS = 512;             // main (256) + corr (256)
 constexpr uint32_t I3_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
@@ -116,7 +116,6 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + I3_STAGES;                                      // both CTAs
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;                                         // used in the leader
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
-  float* epi_stage = reinterpret_cast<float*>(smem + I3_STAGES * I3_STAGE_BYTES + 256);      // 4 x [32][33]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ipt = prm.ipt;
@@ -275,14 +274,7 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
         if (owner) {
-          const int rbase = q * 32;
-          const bool tile_ok = m_tile < prm.tiles_m;
-          auto row_pixel = [&](int rr) -> int64_t {
-            const int r2 = rbase + rr;
-            const int y2 = y0 + r2 / prm.TW, x2 = x0 + r2 % prm.TW;
-            return (tile_ok && y2 < prm.H && x2 < prm.W) ? (int64_t)y2 * prm.W + x2 : (int64_t)-1;
-          };
-          epilogue_store_warp32(prm.ep, epi_stage + q * EPI_STAGE_FLOATS, lane, row_pixel, n0 + c, prm.N, v);
+          if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
         } else {
           float4* dst = reinterpret_cast<float4*>(my_slot + (size_t)row * I3_BN + c);
 #pragma unroll
