@@ -198,13 +198,20 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const long long tile_end = (long long)(tile + 1) * ipt;
         long long c = cta + 1;
         while (c < G && c * prm.total_units / G < tile_end) {
-          const long long t0 = clock64();
-          while (ld_acquire_gpu(prm.flags + c) != prm.epoch) {
-            if (clock64() - t0 > 4000000000LL) {
-              printf("[smb] igemm2 stream-K watchdog: CTA %d waiting for partial of CTA %d\n", (int)cta, (int)c);
-              asm volatile("trap;");
+          // lane 0 spins with plain volatile loads (an acquire load per poll costs an L1 invalidate, CCTL.IVALL,
+          // every iteration: 9 % of all samples in the first ncu capture); one acquire per lane once it is set
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile const unsigned int*>(prm.flags + c) != prm.epoch) {
+              __nanosleep(64);
+              if (clock64() - t0 > 4000000000LL) {
+                printf("[smb] igemm2 stream-K watchdog: CTA %d waiting for partial of CTA %d\n", (int)cta, (int)c);
+                asm volatile("trap;");
+              }
             }
           }
+          __syncwarp();
+          (void)ld_acquire_gpu(prm.flags + c);
           ++npeer;
           ++c;
         }

@@ -233,14 +233,19 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         long long c = pair + 1;
         while (c < G && c * prm.total_units / G < tile_end) {
           const unsigned int* f = prm.flags + 2 * c + rank;           // same-rank CTA of the later pair
-          const long long t0 = clock64();
-          while (ld_acquire_gpu3(f) != prm.epoch) {
-            if (clock64() - t0 > 4000000000LL) {
-              printf("[smb] igemm3 stream-K watchdog: CTA %d waiting for partial of CTA %d\n", (int)cta,
-                     (int)(2 * c + rank));
-              asm volatile("trap;");
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile const unsigned int*>(f) != prm.epoch) {
+              __nanosleep(64);
+              if (clock64() - t0 > 4000000000LL) {
+                printf("[smb] igemm3 stream-K watchdog: CTA %d waiting for partial of CTA %d\n", (int)cta,
+                       (int)(2 * c + rank));
+                asm volatile("trap;");
+              }
             }
           }
+          __syncwarp();
+          (void)ld_acquire_gpu3(f);
           ++npeer;
           ++c;
         }
