@@ -14,6 +14,8 @@
 //    accumulate, a systematic bias proportional to the number of accumulate steps times ulp(accumulator)
 //    (measured -2.4e-5 relative on an all-positive K=4608 conv); keeping the small terms out of the large
 //    accumulator cuts the chain on `main` to a third and makes the truncation on `corr` negligible.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "smb_epilogue.cuh"
 #include "smb_kernels.h"
@@ -393,8 +395,16 @@ int launch_igemm_tc2(const Act& a, const PackedB& b, const Epilogue& ep, cudaStr
               b.K);
   SMB_REQUIRE(b.N % 64 == 0, "igemm_tc2: N=%d must be a multiple of 64", b.N);
   if (a.pixels() == 0) return SMB_OK;
-  if (b.N % 256 == 0) return launch_igemm_tc2_bn<256>(a, b, ep, st);
-  if (b.N % 128 == 0) return launch_igemm_tc2_bn<128>(a, b, ep, st);
+  // widest N tile: 256 halves the operand traffic per MMA but its two accumulators (main + corr) fill the TMEM,
+  // so the epilogue cannot overlap the next tile; 128 keeps a double-buffered TMEM.  SMB_IGEMM_MAX_BN overrides.
+  static int max_bn = 0;
+  if (!max_bn) {
+    const char* e = getenv("SMB_IGEMM_MAX_BN");
+    max_bn = e ? atoi(e) : 256;
+    if (max_bn != 64 && max_bn != 128 && max_bn != 256) max_bn = 256;
+  }
+  if (b.N % 256 == 0 && max_bn >= 256) return launch_igemm_tc2_bn<256>(a, b, ep, st);
+  if (b.N % 128 == 0 && max_bn >= 128) return launch_igemm_tc2_bn<128>(a, b, ep, st);
   return launch_igemm_tc2_bn<64>(a, b, ep, st);
 }
 
