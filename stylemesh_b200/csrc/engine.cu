@@ -397,6 +397,17 @@ int smb_ctx_load_vgg(smb_ctx* ctx, const float* const* weights_oihw, const float
       rc = ctx->weights.alloc(&c.w_oihw, n);
       if (rc) return rc;
       SMB_CUDA_CHECK(cudaMemcpy(c.w_oihw, weights_oihw[0], n * sizeof(float), cudaMemcpyHostToDevice));
+      // data-gradient operand of the first layer for the tensor-core path: N = 3 input channels padded to 16
+      // B[tap=r*3+s][n=ci][k=co] = w[co][ci][2-r][2-s]
+      tmp.assign((size_t)9 * 16 * kCout[0], 0.f);
+      for (int r = 0; r < 3; ++r)
+        for (int s2 = 0; s2 < 3; ++s2)
+          for (int ci = 0; ci < 3; ++ci)
+            for (int co = 0; co < kCout[0]; ++co)
+              tmp[((size_t)(r * 3 + s2) * 16 + ci) * kCout[0] + co] =
+                  weights_oihw[0][(((size_t)co * 3 + ci) * 3 + (2 - r)) * 3 + (2 - s2)];
+      rc = upload_packed(ctx->weights, &c.dgrad, tmp, 9, 16, kCout[0]);
+      if (rc) return rc;
     } else {
       pack_fwd(weights_oihw[i], kCout[i], kCin[i], tmp);
       rc = upload_packed(ctx->weights, &c.fwd, tmp, 9, kCout[i], kCin[i]);
@@ -661,7 +672,13 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
   }
   {
     ScopedTimer tm(ctx->timing, CLS_FIRST_DGRAD, st, 2.0 * 27 * 64 * (double)s.H * s.W);
-    rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
+    if (ctx->conv_impl == IMPL_TC || ctx->conv_impl == IMPL_TC_PAIR) {
+      Epilogue ep;                          // tcgen05 implicit GEMM with N padded 3 -> 16, planar fp32 output
+      ep.out_planar3 = d_image;
+      rc = launch_igemm_tc2(s.dz[0], ctx->conv[0].dgrad, ep, st);
+    } else {
+      rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
+    }
   }
   if (rc) return rc;
   for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;

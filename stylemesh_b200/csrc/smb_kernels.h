@@ -65,6 +65,7 @@ struct Epilogue {
   __nv_bfloat16* out_hi = nullptr;
   __nv_bfloat16* out_lo = nullptr;
   float* out_f32 = nullptr;
+  float* out_planar3 = nullptr;           // (3,H,W) fp32: channels 0..2 of the result, planar (first-layer data gradient)
   const float* rowmask = nullptr;         // [P]  (only with outm_*)
   __nv_bfloat16* outm_hi = nullptr;
   __nv_bfloat16* outm_lo = nullptr;

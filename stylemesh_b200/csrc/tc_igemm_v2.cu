@@ -223,6 +223,43 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
       const uint32_t t_corr = t_main + (uint32_t)BN;
+      if constexpr (BN == 16) {
+        // narrow tile (data gradient of the 3-channel first layer, N padded 3 -> 16): main and corr are adjacent
+        // 16-column blocks, one 32-column TMEM load fetches both
+        uint32_t rm[32];
+        tmem_ld_32x32(t_main, rm);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rm[16 + j]);
+        for (int k = 1; k <= npeer; ++k) {
+          const float4* src = reinterpret_cast<const float4*>(prm.ws + (size_t)(cta + k) * I2_BM * BN + (size_t)row * BN);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 a = src[j];
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+          }
+        }
+        if (owner) {
+          if (valid) {
+            if (prm.ep.out_planar3) {            // (3, H, W) fp32 image gradient
+              const int64_t P = (int64_t)prm.H * prm.W;
+              prm.ep.out_planar3[p] = v[0];
+              prm.ep.out_planar3[P + p] = v[1];
+              prm.ep.out_planar3[2 * P + p] = v[2];
+            } else {
+              epilogue_store<16>(prm.ep, p, n0, prm.N, v);
+            }
+          }
+        } else {
+          float4* dst = reinterpret_cast<float4*>(my_slot + (size_t)row * BN);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t rm[32], rc[32];
@@ -253,6 +290,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+      }
       }
       if (!owner) {
         // publish the partial tile: every epilogue thread's stores -> gpu scope, then one release store of the flag
@@ -393,8 +431,9 @@ int launch_igemm_tc2(const Act& a, const PackedB& b, const Epilogue& ep, cudaStr
   SMB_REQUIRE(b.taps == 9 || b.taps == 1, "igemm_tc2: taps must be 1 or 9");
   SMB_REQUIRE(a.C == b.K && b.K % I2_BK == 0, "igemm_tc2: K=%d must equal the activation channels and be a multiple of 64",
               b.K);
-  SMB_REQUIRE(b.N % 64 == 0, "igemm_tc2: N=%d must be a multiple of 64", b.N);
+  SMB_REQUIRE(b.N % 64 == 0 || b.N == 16, "igemm_tc2: N=%d must be a multiple of 64 (or the padded 16)", b.N);
   if (a.pixels() == 0) return SMB_OK;
+  if (b.N == 16) return launch_igemm_tc2_bn<16>(a, b, ep, st);
   // widest N tile: 256 halves the operand traffic per MMA but its two accumulators (main + corr) fill the TMEM,
   // so the epilogue cannot overlap the next tile; 128 keeps a double-buffered TMEM.  SMB_IGEMM_MAX_BN overrides.
   static int max_bn = 0;

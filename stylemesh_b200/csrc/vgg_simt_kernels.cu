@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(Act in, Act out) {
 // one thread per (2x2 window, 8-channel group): reads the four y pixels once, writes the four dz pixels.
 // Windows hanging over an odd trailing row/column carry no pooled gradient (floor mode) but their pixels still get
 // dz = addend masked by ReLU (or zero).
-__global__ void __launch_bounds__(256) maxpool_bwd_relu_kernel(const float* __restrict__ gp,
+__global__ void __launch_bounds__(256, 3) maxpool_bwd_relu_kernel(const float* __restrict__ gp,
                                                                const float* __restrict__ addend, Act y, Act dz) {
   const int groups = y.C >> 3;
   const int Ho = y.H >> 1, Wo = y.W >> 1;
