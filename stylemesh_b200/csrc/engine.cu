@@ -68,7 +68,7 @@ struct DeviceArena {
 };
 
 struct ConvLayer {
-  PackedB fwd, dgrad;
+  PackedB fwd, dgrad;     // conv 0: fwd = [1][64][32] im2col-ordered operand of conv_first_tc, dgrad = N padded to 16
   float* bias = nullptr;
   float* w_oihw = nullptr;   // device copy of the original layout (first layer only)
 };
@@ -397,6 +397,12 @@ int smb_ctx_load_vgg(smb_ctx* ctx, const float* const* weights_oihw, const float
       rc = ctx->weights.alloc(&c.w_oihw, n);
       if (rc) return rc;
       SMB_CUDA_CHECK(cudaMemcpy(c.w_oihw, weights_oihw[0], n * sizeof(float), cudaMemcpyHostToDevice));
+      // forward operand of the first layer for conv_first_tc: [n=co][k = ci*9 + r*3 + s], K padded 27 -> 32
+      tmp.assign((size_t)kCout[0] * 32, 0.f);
+      for (int co = 0; co < kCout[0]; ++co)
+        for (int k = 0; k < 27; ++k) tmp[(size_t)co * 32 + k] = weights_oihw[0][(size_t)co * 27 + k];
+      rc = upload_packed(ctx->weights, &c.fwd, tmp, 1, kCout[0], 32);
+      if (rc) return rc;
       // data-gradient operand of the first layer for the tensor-core path: N = 3 input channels padded to 16
       // B[tap=r*3+s][n=ci][k=co] = w[co][ci][2-r][2-s]
       tmp.assign((size_t)9 * 16 * kCout[0], 0.f);
@@ -462,7 +468,11 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
     ep.out_hi = s.y[0].hi;
     ep.out_lo = s.y[0].lo;
     ScopedTimer tm(ctx->timing, CLS_CONV_FIRST, st, 2.0 * 27 * 64 * (double)s.H * s.W);
-    int rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
+    int rc;
+    if (ctx->conv_impl == IMPL_TC || ctx->conv_impl == IMPL_TC_PAIR)
+      rc = launch_conv_first_tc(image, s.H, s.W, ctx->conv[0].fwd.hi, ctx->conv[0].fwd.lo, ctx->conv[0].bias, ep, st);
+    else
+      rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
     if (rc) return rc;
   }
   for (int i = 1; i <= last_conv; ++i) {

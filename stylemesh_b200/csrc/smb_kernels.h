@@ -83,6 +83,9 @@ int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStr
 int launch_conv_first_fwd(const float* img, int H, int W, const float* w_oihw, const float* bias, int Cout,
                           const Epilogue& ep, cudaStream_t st);
 int launch_conv_first_dgrad(const Act& dz, const float* w_oihw, int Cout, float* dimg, cudaStream_t st);
+// tcgen05 version of the first layer: w_hi/w_lo = [64][32] bf16 (k = ci*9 + r*3 + s, zero padded to 32)
+int launch_conv_first_tc(const float* img, int H, int W, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                         const float* bias, const Epilogue& ep, cudaStream_t st);
 
 int launch_maxpool_fwd(const Act& in, const Act& out, cudaStream_t st);
 // dz[p][c] = y[p][c] > 0 ? (p is first arg-max of its 2x2 window ? g[window][c] : 0) + addend[p][c] : 0
