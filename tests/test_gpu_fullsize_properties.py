@@ -75,7 +75,8 @@ def test_backward_is_linear_in_the_loss_weight_and_deterministic(engine):
         engine.content_term(slot, 9, T, mask, coef, 2 * coef, acc)
         outs.append((engine.backward(slot, H, W).clone(), float(acc)))
     (g1, l1), (g2, l2), (g3, l3) = outs
-    assert torch.equal(g1, g3) and l1 == l3
+    assert torch.equal(g1, g3)                      # the gradient path has no atomics: bit-identical replays
+    assert abs(l1 - l3) <= 1e-6 * abs(l1)           # the scalar loss is a float-atomic sum over blocks
     assert abs(l2 - 2 * l1) <= 1e-5 * abs(l2)
     assert (g2 - 2 * g1).norm() <= 1e-4 * g2.norm()
     assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
