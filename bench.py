@@ -239,14 +239,11 @@ def run_ours(args):
             float(one_step(mdl, opt, b, i).detach())
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        from stylemesh_b200.lightning_shim import DevicePrefetcher
         e0.record()
-        # every step: H2D of that step's full 13-tuple from pinned memory (prefetched one step ahead on a copy
-        # stream, as the Trainer does), the step through the public API, D2H read of the 4 loss terms
-        feed = DevicePrefetcher((pinned[i % nv].as_batch() for i in range(args.steps)), device)
-        for i, b in enumerate(feed):
+        for i in range(args.steps):
+            b = pinned[i % nv].to(device, non_blocking=True).as_batch()         # H2D of this step's view
             loss = one_step(mdl, opt, b, i)
-            _ = mdl._loss_buf.to("cpu")
+            _ = mdl._loss_buf.to("cpu")                                         # D2H read of the step's 4 loss terms
         e1.record()
         barrier()
         ems = torch.tensor([e0.elapsed_time(e1)], device=device)

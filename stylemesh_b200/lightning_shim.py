@@ -111,48 +111,6 @@ def _to_device(obj: Any, device, _top: bool = True):
     return obj
 
 
-class DevicePrefetcher:
-    """Iterates over host batches (pinned tensors) and keeps ONE batch in flight on a side stream, so that the
-    host->device copy of view i+1 overlaps the kernels of view i (what a pinned-memory DataLoader + Lightning's
-    batch transfer do for the reference).  Every batch is still copied in full, every step."""
-
-    def __init__(self, batches, device):
-        self._it = iter(batches)
-        self._device = device
-        self._stream = torch.cuda.Stream(device=device)
-        self._next = None
-        self._preload()
-
-    def _preload(self):
-        try:
-            host = next(self._it)
-        except StopIteration:
-            self._next = None
-            return
-        with torch.cuda.stream(self._stream):
-            self._next = _to_device(host, self._device)
-
-    def __iter__(self):
-        return self
-
-    def __next__(self):
-        if self._next is None:
-            raise StopIteration
-        cur = torch.cuda.current_stream(self._device)
-        cur.wait_stream(self._stream)
-        batch = self._next
-
-        def _keep(o):
-            if isinstance(o, torch.Tensor) and o.is_cuda:
-                o.record_stream(cur)
-            elif isinstance(o, (list, tuple)):
-                for x in o:
-                    _keep(x)
-        _keep(batch)
-        self._preload()
-        return batch
-
-
 class Trainer:
     _FLAGS = [("--gpus", int, 1), ("--max_epochs", int, 1), ("--default_root_dir", str, "."),
               ("--limit_train_batches", int, -1), ("--limit_val_batches", int, -1), ("--num_sanity_val_steps", int, 0),
@@ -202,10 +160,12 @@ class Trainer:
             model.current_epoch = epoch
             model.on_train_epoch_start()
             model.train()
-            mine = ((i, b) for i, b in enumerate(train_loader)
-                    if not (0 <= self.limit_train_batches <= i) and i % self.world_size == self.rank)
-            mine = list(mine)                                       # view sharding: rank r owns views r, r+N, ...
-            for (batch_idx, _), batch in zip(mine, DevicePrefetcher((b for _, b in mine), device)):
+            for batch_idx, batch in enumerate(train_loader):
+                if 0 <= self.limit_train_batches <= batch_idx:
+                    break
+                if batch_idx % self.world_size != self.rank:      # view sharding: rank r owns views r, r+N, ...
+                    continue
+                batch = _to_device(batch, device)
                 optimizer.zero_grad()
                 out = model.training_step(batch, batch_idx)
                 out["loss"].backward()
