@@ -225,6 +225,28 @@ def run_ours(args):
     total_ms = float(ms)
     value = world * args.steps / (total_ms / 1e3)
 
+    # ------------------------------------------------ extra: content-target cache on -------------
+    # VGG(target)[r42] is constant per view; real runs repeat each view 20-100x (index_repeat).  NOT the headline.
+    cached = None
+    if not args.cache_content_targets:
+        mdl.vgg_loss.cache_content_targets = True
+        for i in range(nv):
+            one_step(mdl, opt, dev_batches[i % nv], i)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(args.steps):
+            one_step(mdl, opt, dev_batches[i % nv], i)
+        c1.record()
+        barrier()
+        cms = torch.tensor([c0.elapsed_time(c1)], device=device)
+        if world > 1:
+            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+        cached = {"value": world * args.steps / (float(cms) / 1e3), "unit": UNIT, "ms_per_step": float(cms) / args.steps,
+                  "note": "same step with VGG(target) features cached per view (opt-in cache_content_targets)"}
+        mdl.vgg_loss.cache_content_targets = False
+        mdl.vgg_loss._content_cache.clear()
+
     # ------------------------------------------------ e2e leg (host buffers through the public API) -----------
     e2e = None
     if not args.no_e2e:
@@ -300,7 +322,7 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (tensor-core convs/Gram as 3x bf16 split products, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roof, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu,
+        "roofline": roof, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu, "with_cached_content_targets": cached,
         "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "tc"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
     }
     return line
