@@ -196,7 +196,7 @@ static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& ou
 }
 
 static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  if (impl == IMPL_TC_PAIR) return (b.N % 256 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
+  if (impl == IMPL_TC_PAIR) return (b.N % 128 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
   return launch_igemm_simt(a, b, ep, st);

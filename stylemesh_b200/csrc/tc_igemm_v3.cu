@@ -10,6 +10,8 @@
 // Everything else is igemm_tc2: TMA boxes with out-of-bounds zero fill as conv padding, bf16 hi/lo three-pass
 // products into main/corr TMEM accumulators, stream-K over (pair-tile, K-iteration) units with first-K-part
 // ownership and epoch-flag fix-ups, fused epilogue.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "smb_epilogue.cuh"
 #include "smb_kernels.h"
@@ -19,14 +21,18 @@ using namespace tc;
 
 constexpr int I3_THREADS = 192;
 constexpr int I3_BM = 128;                    // rows per CTA (the pair covers 256)
-constexpr int I3_BN = 256;
 constexpr int I3_BK = 64;
 constexpr int I3_A_BYTES = I3_BM * I3_BK * 2;           // 16 KiB per plane
-constexpr int I3_B_BYTES = (I3_BN / 2) * I3_BK * 2;     // 16 KiB per plane (this CTA's half of B)
-constexpr int I3_STAGE_BYTES = 2 * I3_A_BYTES + 2 * I3_B_BYTES;   // 64 KiB
-constexpr int I3_STAGES = 3;
 constexpr int I3_SMEM_EXTRA = 1024 + 256;
-constexpr int I3_TMEM_COLS = 512;             // main (256) + corr (256)
+constexpr int I3_TMEM_COLS = 512;             // NBUF x (main + corr)
+
+template <int BN>
+struct I3Cfg {
+  static constexpr int B_BYTES = (BN / 2) * I3_BK * 2;                 // this CTA's half of B, per plane
+  static constexpr int STAGE_BYTES = 2 * I3_A_BYTES + 2 * B_BYTES;     // 48 KiB (BN=128) / 64 KiB (BN=256)
+  static constexpr int STAGES = 196608 / STAGE_BYTES;                  // 4 / 3
+  static constexpr int NBUF = (512 / (2 * BN)) >= 2 ? 2 : 1;           // double-buffered accumulators for BN=128
+};
 constexpr uint32_t I3_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 struct IGemm3Params {
@@ -100,10 +106,16 @@ __device__ __forceinline__ void st_release_gpu3(unsigned int* p, unsigned int v)
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I3_THREADS, 1)
 igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const IGemm3Params prm) {
+  using Cfg = I3Cfg<BN>;
+  constexpr int I3_BN = BN;
+  constexpr int I3_B_BYTES = Cfg::B_BYTES;
+  constexpr int I3_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int I3_STAGES = Cfg::STAGES;
   const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
   const long long G = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const long long cta = blockIdx.x;
@@ -113,9 +125,9 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + I3_STAGES * I3_STAGE_BYTES);   // used in the leader
   uint64_t* empty_bar = full_bar + I3_STAGES;                                           // both CTAs
-  uint64_t* tmem_full_bar = empty_bar + I3_STAGES;                                      // both CTAs
-  uint64_t* tmem_empty_bar = tmem_full_bar + 1;                                         // used in the leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + I3_STAGES;                                      // [2] both CTAs
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                                         // [2] used in the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ipt = prm.ipt;
@@ -129,8 +141,10 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 8);            // 4 epilogue warps of each CTA
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);      // 4 epilogue warps of each CTA
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -177,10 +191,12 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int ks = (int)(u % ipt);
         const long long left = u1 - u;
         const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
-        mbar_wait(tmem_empty_bar, ((uint32_t)seg & 1u) ^ 1u, 32);      // both epilogues drained the accumulators
+        const int buf = seg % Cfg::NBUF;
+        const uint32_t use = (uint32_t)(seg / Cfg::NBUF);
+        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u, 32);          // both epilogues drained this buffer
         tc_fence_after();
-        const uint32_t t_main = tmem_base;
-        const uint32_t t_corr = tmem_base + (uint32_t)I3_BN;
+        const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * I3_BN);
+        const uint32_t t_corr = t_main + (uint32_t)I3_BN;
         for (int it = ks; it < ke; ++it, ++g) {
           const int stage = (int)(g % I3_STAGES);
           const uint32_t phase = (uint32_t)(g / I3_STAGES) & 1u;
@@ -203,7 +219,7 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
           umma_commit_2sm_mc(&empty_bar[stage]);      // frees this stage in BOTH CTAs
         }
-        umma_commit_2sm_mc(tmem_full_bar);            // accumulators complete, both CTAs
+        umma_commit_2sm_mc(&tmem_full_bar[buf]);      // accumulators complete, both CTAs
         u += (ke - ks);
       }
     }
@@ -219,6 +235,8 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const long long left = u1 - u;
       const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
       const bool owner = (ks == 0);
+      const int buf = seg % Cfg::NBUF;
+      const uint32_t use = (uint32_t)(seg / Cfg::NBUF);
       const int pm = tile / prm.tiles_n, n_tile = tile % prm.tiles_n;
       const int m_tile = 2 * pm + (int)rank;
       const int y0 = (m_tile / prm.tiles_x) * prm.TH, x0 = (m_tile % prm.tiles_x) * prm.TW;
@@ -251,9 +269,9 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
 
-      mbar_wait(tmem_full_bar, (uint32_t)seg & 1u, 34);
+      mbar_wait(&tmem_full_bar[buf], use & 1u, 34);
       tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * I3_BN);
       const uint32_t t_corr = t_main + (uint32_t)I3_BN;
 #pragma unroll 1
       for (int c = 0; c < I3_BN; c += 32) {
@@ -264,7 +282,7 @@ igemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (c + 32 >= I3_BN) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cta(tmem_empty_bar, 0);          // the leader's barrier collects 8 arrivals
+          if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[buf], 0);    // the leader's barrier collects 8 arrivals
         }
         float v[32];
 #pragma unroll
@@ -323,11 +341,12 @@ static void pick_patch3(int H, int W, int& TH, int& TW) {
   TW = best_tw;
 }
 
-int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  SMB_REQUIRE(b.taps == 9 || b.taps == 1, "igemm_tc3: taps must be 1 or 9");
-  SMB_REQUIRE(a.C == b.K && b.K % I3_BK == 0 && b.N % I3_BN == 0,
-              "igemm_tc3: K=%d must be a multiple of 64 and N=%d a multiple of 256", b.K, b.N);
-  if (a.pixels() == 0) return SMB_OK;
+template <int BN>
+static int launch_igemm_tc3_bn(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  using Cfg = I3Cfg<BN>;
+  constexpr int I3_BN = BN;
+  constexpr int I3_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int I3_STAGES = Cfg::STAGES;
   IGemm3Params prm;
   int rc = igemm_streamk_workspace(&prm.ws, &prm.flags, &prm.epoch);
   if (rc) return rc;
@@ -367,7 +386,7 @@ int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStr
   const int smem_bytes = I3_STAGES * I3_STAGE_BYTES + I3_SMEM_EXTRA;
   static bool attr_set = false;
   if (!attr_set) {
-    SMB_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SMB_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   static int num_sms = 0;
@@ -379,9 +398,24 @@ int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStr
   }
   long long pairs = std::min<long long>(num_sms / 2, prm.total_units);
   pairs = std::max<long long>(1, std::min<long long>(pairs, std::max<long long>(pair_tiles, prm.total_units / 16)));
-  igemm_tc3_kernel<<<(unsigned)(2 * pairs), I3_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
+  igemm_tc3_kernel<BN><<<(unsigned)(2 * pairs), I3_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
+}
+
+int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  SMB_REQUIRE(b.taps == 9 || b.taps == 1, "igemm_tc3: taps must be 1 or 9");
+  SMB_REQUIRE(a.C == b.K && b.K % I3_BK == 0 && b.N % 128 == 0,
+              "igemm_tc3: K=%d must be a multiple of 64 and N=%d a multiple of 128", b.K, b.N);
+  if (a.pixels() == 0) return SMB_OK;
+  static int want_bn = 0;
+  if (!want_bn) {
+    const char* e = getenv("SMB_IGEMM_PAIR_BN");
+    want_bn = e ? atoi(e) : 128;                 // 128: double-buffered accumulators (epilogue overlaps the MMAs)
+    if (want_bn != 128 && want_bn != 256) want_bn = 128;
+  }
+  if (want_bn == 256 && b.N % 256 == 0) return launch_igemm_tc3_bn<256>(a, b, ep, st);
+  return launch_igemm_tc3_bn<128>(a, b, ep, st);
 }
 
 }  // namespace smb
