@@ -38,6 +38,7 @@ struct IGemm2Params {
   float* ws;                  // [grid][128][BN] fp32 partial tiles
   unsigned int* flags;        // [grid]
   unsigned int epoch;
+  int dbg;                    // timing experiments only (SMB_IGEMM_DEBUG): 1 = hi*hi MMA only, 2 = no MMAs at all
   Epilogue ep;
 };
 
@@ -159,9 +160,11 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint64_t dbh = make_smem_desc_sw128(b_hi + k * 32, 16, 1024);
             const uint64_t dbl = make_smem_desc_sw128(b_lo + k * 32, 16, 1024);
             const uint32_t acc = (uint32_t)((it > ks) || (k > 0));
-            umma_f16(t_corr, dal, dbh, idesc, acc);
-            umma_f16(t_corr, dah, dbl, idesc, 1u);
-            umma_f16(t_main, dah, dbh, idesc, acc);
+            if (prm.dbg == 0) {
+              umma_f16(t_corr, dal, dbh, idesc, acc);
+              umma_f16(t_corr, dah, dbl, idesc, 1u);
+            }
+            if (prm.dbg <= 1) umma_f16(t_main, dah, dbh, idesc, acc);
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -383,6 +386,12 @@ static int launch_igemm_tc2_bn(const Act& a, const PackedB& b, const Epilogue& e
   prm.epoch = ++g_sk.epoch;
   if (prm.epoch == 0) prm.epoch = ++g_sk.epoch;      // 0 is the "never written" value of the flags
   prm.ep = ep;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("SMB_IGEMM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  prm.dbg = dbg;
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   {
