@@ -17,6 +17,7 @@ IMPL_SIMT = 0
 IMPL_TC = 1
 IMPL_TC_V1 = 2
 IMPL_TC_PAIR = 3
+IMPL_TC_HALO = 4
 
 # (name, restype, argtypes) — must list every symbol of include/stylemesh_b200.h (checked by tests/test_abi.py)
 _f = C.c_float

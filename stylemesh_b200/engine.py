@@ -132,6 +132,8 @@ def _impl_from_env(name: str, default: int) -> int:
         return _abi.IMPL_TC_V1
     if v in ("pair", "tc_pair", "tc3", "3"):
         return _abi.IMPL_TC_PAIR
+    if v in ("halo", "tc_halo", "tc4", "4"):
+        return _abi.IMPL_TC_HALO
     if v in ("simt", "0"):
         return _abi.IMPL_SIMT
     raise ValueError(f"{name}={v!r}: expected 'tc' or 'simt'")
