@@ -7,7 +7,9 @@
 // pixels nine times (once per tap, shifted by one pixel).  Here a 16 x 8-pixel output tile loads its (16+2) x (8+2)
 // halo once per 64-channel chunk — 18 row boxes of 10 pixels, each at a 2 KiB pitch so that every 8-pixel run is a
 // 1024-byte-aligned swizzle atom — and the tap (dy, dx) is just a different UMMA descriptor on the same tile:
-//     start = base + dy * 2048 + dx * 128,  stride between 8-row groups (SBO) = 2048,  base_offset = dx.
+//     start = base + dy * pitch + dx * 128,  stride between 8-row groups (SBO) = pitch,  base_offset = 0
+// (verified on B200: the tensor core applies the 128-byte swizzle on absolute shared-memory address bits, so any
+//  128-byte-aligned start and any row pitch — 2048 or the dense 1280 — read back exactly what TMA wrote).
 // Operand bytes per (tile, K-chunk) at BN = 128: 46 KB (A halo) + 9 x 32 KB (B) = 334 KB instead of 9 x 64 = 576 KB.
 //
 // Everything else is igemm_tc2: bf16 hi/lo three-pass products into main/corr TMEM accumulators (double buffered),
@@ -37,7 +39,7 @@ struct IGemm4Params {
   float* ws;
   unsigned int* flags;
   unsigned int epoch;
-  int desc_mode;              // experiment knob: 0 = base_offset = (start >> 7) & 7 (default), 1 = base_offset = 0
+  int desc_mode;              // 1 = descriptor base_offset 0 (correct: verified on B200), 0 = (start >> 7) & 7 (wrong)
   int row_pitch;              // bytes between halo rows in smem: 2048 (1 KiB-aligned 8-pixel atoms) or 1280 (dense)
   int nb;                     // B ring stages (one tap each)
   Epilogue ep;
@@ -317,14 +319,14 @@ static int launch_igemm_halo_bn(const Act& a, const PackedB& b, const Epilogue& 
   static int desc_mode = -1;
   if (desc_mode < 0) {
     const char* e = getenv("SMB_HALO_DESC_MODE");
-    desc_mode = e ? atoi(e) : 0;
+    desc_mode = e ? atoi(e) : 1;     // measured: the tensor core swizzles on absolute smem address bits -> base_offset 0
   }
   prm.desc_mode = desc_mode;
   static int pitch = 0;
   if (!pitch) {
     const char* e = getenv("SMB_HALO_PITCH");
-    pitch = e ? atoi(e) : 2048;
-    if (pitch != 2048 && pitch != 1280) pitch = 2048;
+    pitch = e ? atoi(e) : 1280;      // dense halo rows work too (SBO = 1280) and leave room for a deeper B ring
+    if (pitch != 2048 && pitch != 1280) pitch = 1280;
   }
   prm.row_pitch = pitch;
   const int a_plane = (I4_HR * pitch + 1023) & ~1023;
