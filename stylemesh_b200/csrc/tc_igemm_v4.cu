@@ -73,6 +73,7 @@ __device__ __forceinline__ void st_release_gpu4(unsigned int* p, unsigned int v)
 template <int BN>
 __global__ void __launch_bounds__(I4_THREADS, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmA_row_hi, const __grid_constant__ CUtensorMap tmA_row_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const IGemm4Params prm) {
   using Cfg = I4Cfg<BN>;
@@ -102,6 +103,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmA_row_hi);
+    tma_prefetch_desc(&tmA_row_lo);
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
     for (int s = 0; s < 2; ++s) {
@@ -127,24 +130,38 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // Program order: A(u0); then per unit u: B taps 0..8, with A(u+1) issued after tap 2 so that the halo of the next
+    // K-chunk is in flight long before the tensor pipe needs it (it only needs the other A buffer to be drained).
     if (elect_one()) {
-      long long ga = 0, gb = 0;
-      for (long long u = u0; u < u1; ++u, ++ga) {
+      long long ga_issue = 0, gb = 0;
+      auto issue_A = [&](long long u) {
         const int tile = (int)(u / ipt), kc = (int)(u % ipt);
-        const int m_tile = tile / prm.tiles_n, n_tile = tile % prm.tiles_n;
+        const int m_tile = tile / prm.tiles_n;
         const int y0 = (m_tile / prm.tiles_x) * I4_TH, x0 = (m_tile % prm.tiles_x) * I4_TW;
-        const int abuf = (int)(ga & 1);
-        mbar_wait(&a_empty[abuf], (uint32_t)((ga >> 1) & 1) ^ 1u, 51);
+        const int abuf = (int)(ga_issue & 1);
+        mbar_wait(&a_empty[abuf], (uint32_t)((ga_issue >> 1) & 1) ^ 1u, 51);
         mbar_arrive_expect_tx(&a_full[abuf], I4_A_TX);
         uint8_t* ah = sA + abuf * I4_A_BUF;
         uint8_t* al = ah + I4_A_PLANE;
+        if (I4_ROW_PITCH == I4_HW * 128) {      // dense rows: the whole 18 x 10-pixel halo is ONE box per plane
+          tma_load_3d(ah, &tmA_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
+          tma_load_3d(al, &tmA_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
+        } else {
 #pragma unroll 1
-        for (int r = 0; r < I4_HR; ++r) {      // halo row r = image row y0 - 1 + r, pixels x0 - 1 .. x0 + 8
-          tma_load_3d(ah + r * I4_ROW_PITCH, &tmA_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1 + r);
-          tma_load_3d(al + r * I4_ROW_PITCH, &tmA_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1 + r);
+          for (int r = 0; r < I4_HR; ++r) {     // halo row r = image row y0 - 1 + r, pixels x0 - 1 .. x0 + 8
+            tma_load_3d(ah + r * I4_ROW_PITCH, &tmA_row_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1 + r);
+            tma_load_3d(al + r * I4_ROW_PITCH, &tmA_row_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1 + r);
+          }
         }
+        ++ga_issue;
+      };
+      issue_A(u0);
+      for (long long u = u0; u < u1; ++u) {
+        const int tile = (int)(u / ipt), kc = (int)(u % ipt);
+        const int n_tile = tile % prm.tiles_n;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap, ++gb) {
+          if (tap == 3 && u + 1 < u1) issue_A(u + 1);
           const int bs = (int)(gb % NB);
           mbar_wait(&b_empty[bs], (uint32_t)((gb / NB) & 1) ^ 1u, 52);
           mbar_arrive_expect_tx(&b_full[bs], Cfg::B_STAGE);
@@ -333,14 +350,19 @@ static int launch_igemm_halo_bn(const Act& a, const PackedB& b, const Epilogue& 
   prm.nb = std::min(I4_MAX_NB, (I4_SMEM_TOTAL - 4 * a_plane) / Cfg::B_STAGE);
   SMB_REQUIRE(prm.nb >= 2, "igemm_halo: shared memory budget leaves %d B stages", prm.nb);
 
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  CUtensorMap tmA_hi, tmA_lo, tmA_row_hi, tmA_row_lo, tmB_hi, tmB_lo;
   {
     const uint64_t dims[3] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H};
     const uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2};
-    const uint32_t box[3] = {64u, (uint32_t)I4_HW, 1u};            // one halo row: 10 pixels x 64 channels
+    const uint32_t box[3] = {64u, (uint32_t)I4_HW, (uint32_t)I4_HR};   // whole halo: 18 rows x 10 pixels x 64 channels
     rc = make_tmap_bf16(&tmA_hi, a.hi, 3, dims, strides, box);
     if (rc) return rc;
     rc = make_tmap_bf16(&tmA_lo, a.lo, 3, dims, strides, box);
+    if (rc) return rc;
+    const uint32_t rbox[3] = {64u, (uint32_t)I4_HW, 1u};               // one halo row (2048-byte pitch variant)
+    rc = make_tmap_bf16(&tmA_row_hi, a.hi, 3, dims, strides, rbox);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmA_row_lo, a.lo, 3, dims, strides, rbox);
     if (rc) return rc;
   }
   {
@@ -367,7 +389,8 @@ static int launch_igemm_halo_bn(const Act& a, const PackedB& b, const Epilogue& 
     if (num_sms > 148) num_sms = 148;
   }
   const int grid = (int)std::max<long long>(1, std::min<long long>(num_sms, prm.total_units));
-  igemm_halo_kernel<BN><<<grid, I4_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
+  igemm_halo_kernel<BN><<<grid, I4_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmA_row_hi, tmA_row_lo, tmB_hi, tmB_lo,
+                                                              prm);
   SMB_LAUNCH_CHECK();
   return SMB_OK;
 }
