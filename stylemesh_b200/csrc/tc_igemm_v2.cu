@@ -120,6 +120,10 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int dy = (prm.taps == 9) ? tap / 3 - 1 : 0;
         const int dx = (prm.taps == 9) ? tap % 3 - 1 : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1u, 21);
+        if (prm.dbg == 4) {                 // timing experiment: no operand traffic at all
+          mbar_arrive(&full_bar[stage]);
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         tma_load_3d(st, &tmA_hi, &full_bar[stage], kc * I2_BK, x0 + dx, y0 + dy);
@@ -160,11 +164,11 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint64_t dbh = make_smem_desc_sw128(b_hi + k * 32, 16, 1024);
             const uint64_t dbl = make_smem_desc_sw128(b_lo + k * 32, 16, 1024);
             const uint32_t acc = (uint32_t)((it > ks) || (k > 0));
-            if (prm.dbg == 0) {
+            if (prm.dbg == 0 || prm.dbg >= 3) {
               umma_f16(t_corr, dal, dbh, idesc, acc);
               umma_f16(t_corr, dah, dbl, idesc, 1u);
             }
-            if (prm.dbg <= 1) umma_f16(t_main, dah, dbh, idesc, acc);
+            if (prm.dbg <= 1 || prm.dbg >= 3) umma_f16(t_main, dah, dbh, idesc, acc);
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -287,7 +291,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
         if (owner) {
-          if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
+          if (valid && prm.dbg != 3) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);   // dbg 3: no epilogue math/stores
         } else {
           float4* dst = reinterpret_cast<float4*>(my_slot + (size_t)row * BN + c);
 #pragma unroll
