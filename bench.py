@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
-    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc1", "pair", "halo", "simt"])
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc1", "pair", "halo", "ph", "simt"])
     return ap.parse_args()
 
 

@@ -32,6 +32,7 @@ extern "C" {
 #define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (default product; convs: persistent stream-K kernel) */
 #define SMB_IMPL_TC_V1 2 /* convs only: first-generation tcgen05 kernel, one output tile per CTA             */
 #define SMB_IMPL_TC_HALO 4 /* convs only: 3x3 convs load the activation halo once per K-chunk and reuse it for all 9 taps */
+#define SMB_IMPL_TC_PH 5 /* convs only: CTA pair + activation halo + TMA-store epilogue for 3x3 convs, stream-K kernel otherwise */
 #define SMB_IMPL_TC_PAIR 3 /* convs only: cta_group::2 CTA-pair kernel for N % 256 == 0, stream-K kernel otherwise */
 
 typedef struct smb_ctx smb_ctx;
@@ -142,6 +143,11 @@ int smb_ctx_read_timing(smb_ctx* ctx, float* ms, double* flops, int* launches, i
 
 /* Bytes of device memory currently owned by the context. */
 int64_t smb_ctx_device_bytes(smb_ctx* ctx);
+
+/* Profiling aid: when `buf` (device memory, >= 148 * 16 uint64) is non-NULL every following stream-K conv launch
+ * writes a per-CTA timeline (clock64 / globaltimer stamps and barrier-wait totals, layout in tc_igemm_v2.cu) into
+ * it; NULL switches the tracing off again.  Used by tools/gpu_trace_probe.py, never on in tests or the bench. */
+int smb_debug_set_igemm_trace(void* buf);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Unit-level entry points (used by the parity tests to localise a failure to one kernel).

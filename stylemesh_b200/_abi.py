@@ -18,6 +18,7 @@ IMPL_TC = 1
 IMPL_TC_V1 = 2
 IMPL_TC_PAIR = 3
 IMPL_TC_HALO = 4
+IMPL_TC_PH = 5
 
 # (name, restype, argtypes) — must list every symbol of include/stylemesh_b200.h (checked by tests/test_abi.py)
 _f = C.c_float
@@ -53,6 +54,7 @@ PROTOTYPES = [
     ("smb_ctx_set_timing", _i, [_p, _i]),
     ("smb_ctx_read_timing", _i, [_p, _p, _p, _p, _i]),
     ("smb_ctx_device_bytes", _i64, [_p]),
+    ("smb_debug_set_igemm_trace", _i, [_p]),
     ("smb_unit_conv3x3", _i, [_i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     ("smb_unit_maxpool", _i, [_p, _i, _i, _i, _p, _p]),
     ("smb_unit_maxpool_bwd", _i, [_p, _p, _i, _i, _i, _p, _p]),

@@ -5,14 +5,15 @@
 
 namespace smb {
 
-// Apply the epilogue to NV (multiple of 4) consecutive channels n..n+NV-1 of pixel p and store.
-// All row pointers are [P][N] with N a multiple of 4 and n a multiple of 4 => 16-byte fp32 / 8-byte bf16 accesses
-// (NV a multiple of 8 and n a multiple of 8 upgrades bf16 accesses to 16 bytes).
+// The arithmetic half of the epilogue on NV (multiple of 4) consecutive channels n..n+NV-1 of pixel p:
+//   v *= rowscale[p]; v += bias[n]; v += addend[p][n]; v = sign_hi[p][n] > 0 ? v : 0; v = relu ? max(v, 0) : v
+// `in_image` = p is a real pixel (per-pixel operands are only read then; bias is per channel and always applied).
 template <int NV>
-__device__ __forceinline__ void epilogue_store(const Epilogue& ep, int64_t p, int n, int N, float (&v)[NV]) {
+__device__ __forceinline__ void epilogue_apply(const Epilogue& ep, int64_t p, int n, int N, float (&v)[NV],
+                                               bool in_image = true) {
   static_assert(NV % 4 == 0, "NV must be a multiple of 4");
   const int64_t off = p * (int64_t)N + n;
-  if (ep.rowscale) {
+  if (ep.rowscale && in_image) {
     const float rs = __ldg(ep.rowscale + p);
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] *= rs;
@@ -24,14 +25,14 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, int64_t p, in
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (ep.addend) {
+  if (ep.addend && in_image) {
 #pragma unroll
     for (int j = 0; j < NV; j += 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(ep.addend + off + j));
       v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
     }
   }
-  if (ep.sign_hi) {
+  if (ep.sign_hi && in_image) {
 #pragma unroll
     for (int j = 0; j < NV; j += 4) {
       const uint2 s = __ldg(reinterpret_cast<const uint2*>(ep.sign_hi + off + j));
@@ -47,6 +48,15 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, int64_t p, in
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
   }
+}
+
+// Apply the epilogue to NV (multiple of 4) consecutive channels n..n+NV-1 of pixel p and store.
+// All row pointers are [P][N] with N a multiple of 4 and n a multiple of 4 => 16-byte fp32 / 8-byte bf16 accesses
+// (NV a multiple of 8 and n a multiple of 8 upgrades bf16 accesses to 16 bytes).
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const Epilogue& ep, int64_t p, int n, int N, float (&v)[NV]) {
+  const int64_t off = p * (int64_t)N + n;
+  epilogue_apply<NV>(ep, p, n, N, v);
   if (ep.out_f32) {
 #pragma unroll
     for (int j = 0; j < NV; j += 4)

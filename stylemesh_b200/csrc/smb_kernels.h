@@ -71,13 +71,15 @@ struct Epilogue {
   __nv_bfloat16* outm_lo = nullptr;
 };
 
-enum ConvImpl : int { IMPL_SIMT = 0, IMPL_TC = 1, IMPL_TC_V1 = 2, IMPL_TC_PAIR = 3, IMPL_TC_HALO = 4 };
+enum ConvImpl : int { IMPL_SIMT = 0, IMPL_TC = 1, IMPL_TC_V1 = 2, IMPL_TC_PAIR = 3, IMPL_TC_HALO = 4, IMPL_TC_PH = 5 };
 
 // generic 3x3 (taps==9, pad 1) or 1x1 (taps==1) implicit GEMM: out[p][n] = sum_tap sum_k A[p+off(tap)][k] * B[tap][n][k]
 int launch_igemm_simt(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);
 int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);    // v1: one tile per CTA
 int launch_igemm_tc2(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v2: persistent stream-K
 int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v3: v2 on CTA pairs (N % 128 == 0)
+void set_igemm_trace(unsigned long long* buf);   // tc_igemm_v2.cu: per-CTA timeline of the following launches
+int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);    // v5: CTA pair + A halo + TMA-store epilogue (3x3 only)
 int launch_igemm_halo(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);  // v4: 3x3 only, A halo reused by 9 taps
 
 // first layer (3 -> 64) from the fp32 planar image and its data gradient (64 -> 3)

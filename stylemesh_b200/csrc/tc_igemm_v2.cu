@@ -39,6 +39,7 @@ struct IGemm2Params {
   unsigned int* flags;        // [grid]
   unsigned int epoch;
   int dbg;                    // timing experiments only (SMB_IGEMM_DEBUG): 1 = hi*hi MMA only, 2 = no MMAs at all
+  unsigned long long* trace;  // optional [grid][16] per-CTA timeline (smb_debug_set_igemm_trace), nullptr = off
   Epilogue ep;
 };
 
@@ -57,6 +58,15 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// per-CTA timeline slots (tools/gpu_trace_probe.py prints them)
+enum : int { TR_GT_IN = 0, TR_GT_OUT, TR_CLK_IN, TR_CLK_PROLOGUE, TR_CLK_TMA_END, TR_CLK_MMA_FIRST, TR_CLK_MMA_END,
+             TR_CLK_EPI_FIRST, TR_CLK_EPI_END, TR_W_FLAGS, TR_W_TMEM_FULL, TR_W_FULL, TR_W_TMEM_EMPTY, TR_W_EMPTY,
+             TR_CLK_OUT, TR_SMID };
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -81,6 +91,14 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ipt = prm.ipt;
+  unsigned long long* tr = prm.trace ? prm.trace + (size_t)cta * 16 : nullptr;
+  if (tr && threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[TR_GT_IN] = global_ns();
+    tr[TR_CLK_IN] = (unsigned long long)clock64();
+    tr[TR_SMID] = smid;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -105,11 +123,13 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[TR_CLK_PROLOGUE] = (unsigned long long)clock64();
 
   if (warp == 0) {
     // ===================== TMA producer: streams every K-iteration of the CTA's unit range =====================
     if (elect_one()) {
       long long g = 0;
+      long long w_empty = 0;
       for (long long u = u0; u < u1; ++u, ++g) {
         const int stage = (int)(g % Cfg::STAGES);
         const uint32_t phase = (uint32_t)(g / Cfg::STAGES) & 1u;
@@ -119,7 +139,9 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int tap = it / prm.kchunks, kc = it % prm.kchunks;
         const int dy = (prm.taps == 9) ? tap / 3 - 1 : 0;
         const int dx = (prm.taps == 9) ? tap % 3 - 1 : 0;
+        const long long tw0 = tr ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1u, 21);
+        if (tr) w_empty += clock64() - tw0;
         if (prm.dbg == 4) {                 // timing experiment: no operand traffic at all
           mbar_arrive(&full_bar[stage]);
           continue;
@@ -131,6 +153,10 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tma_load_3d(st + 2 * I2_A_BYTES, &tmB_hi, &full_bar[stage], kc * I2_BK, n_tile * BN, tap);
         tma_load_3d(st + 2 * I2_A_BYTES + Cfg::B_BYTES, &tmB_lo, &full_bar[stage], kc * I2_BK, n_tile * BN, tap);
       }
+      if (tr) {
+        tr[TR_CLK_TMA_END] = (unsigned long long)clock64();
+        tr[TR_W_EMPTY] = (unsigned long long)w_empty;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -138,20 +164,29 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(I2_BM, BN, 0, 0);
       long long g = 0;
       int seg = 0;
+      long long w_full = 0, w_tempty = 0;
       for (long long u = u0; u < u1; ++seg) {
         const int ks = (int)(u % ipt);
         const long long left = u1 - u;
         const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
         const int buf = seg % Cfg::NBUF;
         const uint32_t use = (uint32_t)(seg / Cfg::NBUF);
+        const long long tw1 = tr ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u, 22);      // epilogue has drained this buffer
+        if (tr) w_tempty += clock64() - tw1;
         tc_fence_after();
         const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
         const uint32_t t_corr = t_main + (uint32_t)BN;
         for (int it = ks; it < ke; ++it, ++g) {
           const int stage = (int)(g % Cfg::STAGES);
           const uint32_t phase = (uint32_t)(g / Cfg::STAGES) & 1u;
+          const long long tw2 = tr ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase, 23);
+          if (tr) {
+            const long long now = clock64();
+            w_full += now - tw2;
+            if (g == 0) tr[TR_CLK_MMA_FIRST] = (unsigned long long)now;
+          }
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t a_lo = a_hi + I2_A_BYTES;
@@ -175,6 +210,11 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         umma_commit(&tmem_full_bar[buf]);
         u += (ke - ks);
       }
+      if (tr) {
+        tr[TR_CLK_MMA_END] = (unsigned long long)clock64();
+        tr[TR_W_FULL] = (unsigned long long)w_full;
+        tr[TR_W_TMEM_EMPTY] = (unsigned long long)w_tempty;
+      }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -182,6 +222,8 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int row = q * 32 + lane;
     float* my_slot = prm.ws + (size_t)cta * I2_BM * BN;
     int seg = 0;
+    long long w_flags = 0, w_tfull = 0;
+    const bool tr_me = tr && warp == 2 && lane == 0;
     for (long long u = u0; u < u1; ++seg) {
       const int tile = (int)(u / ipt);
       const int ks = (int)(u % ipt);
@@ -203,6 +245,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
       // peers holding the remaining K-range of this tile: CTAs cta+1, cta+2, ... whose range starts inside the tile
       int npeer = 0;
+      const long long tw3 = tr_me ? clock64() : 0;
       if (owner && ke < ipt) {
         const long long tile_end = (long long)(tile + 1) * ipt;
         long long c = cta + 1;
@@ -226,7 +269,12 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
 
+      const long long tw4 = tr_me ? clock64() : 0;
       mbar_wait(&tmem_full_bar[buf], use & 1u, 24);
+      if (tr_me) {
+        w_flags += tw4 - tw3;
+        w_tfull += clock64() - tw4;
+      }
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
       const uint32_t t_corr = t_main + (uint32_t)BN;
@@ -305,12 +353,22 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) st_release_gpu(prm.flags + cta, prm.epoch);
       }
+      if (tr_me && seg == 0) tr[TR_CLK_EPI_FIRST] = (unsigned long long)clock64();
       u += (ke - ks);
+    }
+    if (tr_me) {
+      tr[TR_CLK_EPI_END] = (unsigned long long)clock64();
+      tr[TR_W_FLAGS] = (unsigned long long)w_flags;
+      tr[TR_W_TMEM_FULL] = (unsigned long long)w_tfull;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (tr && threadIdx.x == 0) {
+    tr[TR_CLK_OUT] = (unsigned long long)clock64();
+    tr[TR_GT_OUT] = global_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -341,6 +399,9 @@ struct StreamKWorkspace {
   int device = -1;
 };
 static StreamKWorkspace g_sk;
+static unsigned long long* g_trace = nullptr;      // device buffer of >= 148 * 16 u64, set by smb_debug_set_igemm_trace
+void set_igemm_trace(unsigned long long* buf) { g_trace = buf; }
+unsigned long long* get_igemm_trace() { return g_trace; }
 
 static int ensure_workspace() {
   int dev = 0;
@@ -396,6 +457,7 @@ static int launch_igemm_tc2_bn(const Act& a, const PackedB& b, const Epilogue& e
     dbg = e ? atoi(e) : 0;
   }
   prm.dbg = dbg;
+  prm.trace = g_trace;
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   {

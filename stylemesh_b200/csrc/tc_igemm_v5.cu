@@ -1,0 +1,596 @@
+// igemm_ph_kernel ("pair + halo") — fourth generation of the 3x3 implicit-GEMM conv.
+//
+// What the per-CTA timelines of igemm_tc2 showed (tools/gpu_trace_probe.py, conv3_2 at 480x640, 1.72 GHz):
+//   * the MMA loop takes 77.5 k cycles for 56 k cycles of tensor work: an M=128 x N=128 kind::f16 MMA with both
+//     operands in shared memory reads 8 KB per 64 cycles = the whole 128 B/clk of the SM's shared memory, and the
+//     same memory takes the 83 B/clk TMA fill of a tap-per-stage pipeline (64 KB per 768 MMA-cycles);
+//   * with the MMAs removed the TMA stream alone needs 70 k cycles (68 B/clk/SM from L2), with the TMA removed the
+//     MMAs alone need 70 k: both sides sit at the same wall, which is why neither the halo kernel (less L2 traffic,
+//     same shared-memory reads) nor the CTA-pair kernel (fewer reads, same traffic) moved the time on their own;
+//   * the last tile's epilogue is exposed: 14 k cycles, dominated by 32-way divergent 16-byte global stores.
+// This kernel combines the three fixes:
+//   1. CTA pair (tcgen05 cta_group::2, M = 256): each SM reads its own 128 pixel rows of A and HALF of B per MMA
+//      -> 6 KB per 64 cycles (96 B/clk) at N = 128;
+//   2. activation halo: a 16 x 8-pixel patch loads its 18 x 10 halo once per 64-channel chunk and the nine taps are
+//      shifted UMMA descriptors on it (start = base + dy * 1280 + dx * 128, SBO = 1280; verified on B200 in
+//      igemm_halo_kernel) -> shared-memory fill per SM drops from 64 KB to 21 KB per tap (28 B/clk);
+//   3. epilogue through shared memory: each thread writes its pixel's 64 channels as swizzled 16-byte chunks
+//      (conflict free), one thread issues a TMA tensor store per plane; out-of-image pixels are clipped by TMA.
+// Unchanged: bf16 hi/lo three-pass products into main/corr TMEM accumulators (double buffered), persistent CTAs
+// with stream-K over (pair tile, K-chunk) units, first-K-part ownership with epoch-flag fix-ups, watchdogs.
+#include <cstdlib>
+
+#include "tc_common.cuh"
+#include "smb_epilogue.cuh"
+#include "smb_kernels.h"
+
+namespace smb {
+using namespace tc;
+
+constexpr int I5_THREADS = 192;
+constexpr int I5_BM = 128;                            // pixel rows per CTA (the pair covers 256)
+constexpr int I5_TH = 16, I5_TW = 8;                  // output patch of one CTA: 16 rows x 8 pixels
+constexpr int I5_HR = I5_TH + 2, I5_HW = I5_TW + 2;   // halo: 18 rows x 10 pixels
+constexpr int I5_PITCH = I5_HW * 128;                 // bytes between halo rows (dense)
+constexpr int I5_A_PLANE = (I5_HR * I5_PITCH + 1023) & ~1023;   // 23552
+constexpr int I5_A_BUF = 2 * I5_A_PLANE;              // hi + lo
+constexpr int I5_A_TX = 2 * I5_HR * I5_HW * 128;      // bytes TMA writes per halo and CTA (hi + lo) = 46080
+constexpr int I5_OUT_PLANE = I5_BM * 128;             // 128 pixels x 64 channels bf16 = 16 KiB
+constexpr int I5_OUT_BYTES = 2 * I5_OUT_PLANE;        // hi + lo staging of one 64-channel group
+constexpr int I5_BAR_BYTES = 512;
+constexpr int I5_SMEM_LIMIT = 227 * 1024;
+constexpr int I5_MAX_NB = 8;
+constexpr uint32_t I5_PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in CTA 0 of the pair
+
+template <int BN>
+struct I5Cfg {
+  static constexpr int B_PLANE = (BN / 2) * 128;                 // this CTA's half of the B tile of one tap
+  static constexpr int B_STAGE = 2 * B_PLANE;                    // hi + lo
+  static constexpr int NB_FIT = (I5_SMEM_LIMIT - 1024 - 2 * I5_A_BUF - I5_OUT_BYTES - I5_BAR_BYTES) / B_STAGE;
+  static constexpr int NB = NB_FIT < I5_MAX_NB ? NB_FIT : I5_MAX_NB;
+  static constexpr int SMEM = 1024 + 2 * I5_A_BUF + I5_OUT_BYTES + NB * B_STAGE + I5_BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * 2 * BN) <= 256 ? 256 : 512;   // 2 tile buffers x (main + corr)
+  static_assert(NB >= 4, "B ring too shallow");
+};
+
+struct IGemm5Params {
+  int H, W, tiles_x, tiles_m, tiles_n, kchunks, N;
+  long long total_units;      // pair_tiles * kchunks
+  float* ws;                  // [grid][128][BN] fp32 partial tiles (indexed by CTA id)
+  unsigned int* flags;        // [grid]
+  unsigned int epoch;
+  int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores
+  unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
+  Epilogue ep;
+};
+
+enum : int { T5_GT_IN = 0, T5_GT_OUT, T5_CLK_IN, T5_CLK_PROLOGUE, T5_CLK_TMA_END, T5_CLK_MMA_FIRST, T5_CLK_MMA_END,
+             T5_CLK_EPI_FIRST, T5_CLK_EPI_END, T5_W_FLAGS, T5_W_TMEM_FULL, T5_W_FULL, T5_W_TMEM_EMPTY, T5_W_EMPTY,
+             T5_CLK_OUT, T5_SMID };
+__device__ __forceinline__ unsigned long long i5_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- cta_group::2 / cluster flavours of the building blocks -------------------------------------------------
+__device__ __forceinline__ uint32_t i5_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void i5_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs; the transaction bytes are credited to the barrier of CTA 0 of the pair
+__device__ __forceinline__ void i5_tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & I5_PEER_MASK), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void i5_tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void i5_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void i5_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void i5_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void i5_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void i5_tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void i5_tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void i5_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void i5_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (after all previously issued MMAs completed) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void i5_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void i5_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ unsigned int i5_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void i5_st_release(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// K-major SWIZZLE_128B operand whose 8-row groups are `sbo` bytes apart (1024 for dense tiles, the halo row pitch
+// for the activation operand); base_offset 0: the tensor core swizzles on absolute shared-memory address bits
+__device__ __forceinline__ uint64_t i5_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;                                   // LBO (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void i5_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I5_THREADS, 1)
+igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                const IGemm5Params prm) {
+  using Cfg = I5Cfg<BN>;
+  constexpr int NB = Cfg::NB;
+  const uint32_t rank = i5_ctarank();                 // 0 = leader (issues the MMAs), 1 = peer
+  const long long G = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const long long cta = blockIdx.x;
+  const long long u0 = pair * prm.total_units / G, u1 = (pair + 1) * prm.total_units / G;   // G <= total_units
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                         // [2 bufs][hi, lo][18 halo rows x 1280 B]
+  uint8_t* sOut = sA + 2 * I5_A_BUF;                          // [hi, lo][128 pixels x 128 B]
+  uint8_t* sB = sOut + I5_OUT_BYTES;                          // [NB][hi, lo][BN/2 x 128 B]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + NB * Cfg::B_STAGE);   // [2]  used in the leader
+  uint64_t* a_empty = a_full + 2;                             // [2]  both CTAs
+  uint64_t* b_full = a_empty + 2;                             // [NB] used in the leader
+  uint64_t* b_empty = b_full + I5_MAX_NB;                     // [NB] both CTAs
+  uint64_t* tmem_full_bar = b_empty + I5_MAX_NB;              // [2]  both CTAs
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;               // [2]  used in the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ipt = prm.kchunks;                                // units per pair tile
+  unsigned long long* tr = prm.trace ? prm.trace + (size_t)cta * 16 : nullptr;
+  if (tr && threadIdx.x == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr[T5_GT_IN] = i5_global_ns();
+    tr[T5_CLK_IN] = (unsigned long long)clock64();
+    tr[T5_SMID] = smid;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    if (prm.tma_out) {
+      tma_prefetch_desc(&tmO_hi);
+      tma_prefetch_desc(&tmO_lo);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 8);      // 4 epilogue warps of each CTA
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    i5_tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    i5_tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  i5_cluster_sync();                         // peer barriers are initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[T5_CLK_PROLOGUE] = (unsigned long long)clock64();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own halo, own half of B) =====================
+    // Program order: A(u0); then per unit u: B taps 0..8 with A(u+1) issued after tap 2, so the next halo is in
+    // flight long before the tensor pipe needs it (it only needs the other A buffer to be drained).
+    if (elect_one()) {
+      long long ga = 0, gb = 0, w_empty = 0;
+      auto issue_A = [&](long long u) {
+        const int tile = (int)(u / ipt), kc = (int)(u % ipt);
+        const int m_tile = 2 * (tile / prm.tiles_n) + (int)rank;
+        const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
+        const int abuf = (int)(ga & 1);
+        mbar_wait(&a_empty[abuf], (uint32_t)((ga >> 1) & 1) ^ 1u, 61);
+        if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);      // bytes of both CTAs
+        uint8_t* ah = sA + abuf * I5_A_BUF;
+        i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
+        i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
+        ++ga;
+      };
+      issue_A(u0);
+      for (long long u = u0; u < u1; ++u) {
+        const int tile = (int)(u / ipt), kc = (int)(u % ipt);
+        const int nb0 = (tile % prm.tiles_n) * BN + (int)rank * (BN / 2);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++gb) {
+          if (tap == 3 && u + 1 < u1) issue_A(u + 1);
+          const int bs = (int)(gb % NB);
+          const long long tw0 = tr ? clock64() : 0;
+          mbar_wait(&b_empty[bs], (uint32_t)((gb / NB) & 1) ^ 1u, 62);
+          if (tr) w_empty += clock64() - tw0;
+          if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_STAGE);
+          uint8_t* bh = sB + bs * Cfg::B_STAGE;
+          i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], kc * 64, nb0, tap);
+          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], kc * 64, nb0, tap);
+        }
+      }
+      if (tr) {
+        tr[T5_CLK_TMA_END] = (unsigned long long)clock64();
+        tr[T5_W_EMPTY] = (unsigned long long)w_empty;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * I5_BM, BN, 0, 0);
+      long long ga = 0, gb = 0, w_full = 0, w_tempty = 0;
+      int seg = 0;
+      for (long long u = u0; u < u1; ++seg) {
+        const int ks = (int)(u % ipt);
+        const long long left = u1 - u;
+        const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
+        const int buf = seg & 1;
+        const uint32_t use = (uint32_t)(seg >> 1);
+        const long long tw1 = tr ? clock64() : 0;
+        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u, 63);       // both epilogues drained this buffer
+        if (tr) w_tempty += clock64() - tw1;
+        tc_fence_after();
+        const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
+        const uint32_t t_corr = t_main + (uint32_t)BN;
+        for (int kc = ks; kc < ke; ++kc, ++ga) {
+          const int abuf = (int)(ga & 1);
+          const long long tw2 = tr ? clock64() : 0;
+          mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
+          if (tr) w_full += clock64() - tw2;
+          const uint32_t a_hi = smem_u32(sA + abuf * I5_A_BUF);
+          const uint32_t a_lo = a_hi + I5_A_PLANE;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++gb) {
+            const int bs = (int)(gb % NB);
+            const long long tw3 = tr ? clock64() : 0;
+            mbar_wait(&b_full[bs], (uint32_t)((gb / NB) & 1), 65);
+            if (tr) {
+              const long long now = clock64();
+              w_full += now - tw3;
+              if (gb == 0) tr[T5_CLK_MMA_FIRST] = (unsigned long long)now;
+            }
+            tc_fence_after();
+            const uint32_t a_off = (uint32_t)((tap / 3) * I5_PITCH + (tap % 3) * 128);   // halo coords of the tap
+            const uint32_t b_hi = smem_u32(sB + bs * Cfg::B_STAGE);
+            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dah = i5_desc(a_hi + a_off + k * 32, I5_PITCH);
+              const uint64_t dal = i5_desc(a_lo + a_off + k * 32, I5_PITCH);
+              const uint64_t dbh = i5_desc(b_hi + k * 32, 1024);
+              const uint64_t dbl = i5_desc(b_lo + k * 32, 1024);
+              const uint32_t acc = (uint32_t)((kc > ks) || (tap > 0) || (k > 0));
+              i5_umma(t_corr, dal, dbh, idesc, acc);
+              i5_umma(t_corr, dah, dbl, idesc, 1u);
+              i5_umma(t_main, dah, dbh, idesc, acc);
+            }
+            i5_commit_mc(&b_empty[bs]);          // frees this B stage in BOTH CTAs
+          }
+          i5_commit_mc(&a_empty[abuf]);          // frees this halo buffer in BOTH CTAs
+        }
+        i5_commit_mc(&tmem_full_bar[buf]);       // accumulators complete, both CTAs
+        u += (ke - ks);
+      }
+      if (tr) {
+        tr[T5_CLK_MMA_END] = (unsigned long long)clock64();
+        tr[T5_W_FULL] = (unsigned long long)w_full;
+        tr[T5_W_TMEM_EMPTY] = (unsigned long long)w_tempty;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (each CTA drains its own 128 TMEM lanes) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool epi_leader = (warp == 2 && lane == 0);
+    float* my_slot = prm.ws + (size_t)cta * I5_BM * BN;
+    const uint32_t s_out = smem_u32(sOut);
+    long long w_flags = 0, w_tfull = 0;
+    const bool tr_me = tr && epi_leader;
+    int seg = 0;
+    for (long long u = u0; u < u1; ++seg) {
+      const int tile = (int)(u / ipt);
+      const int ks = (int)(u % ipt);
+      const long long left = u1 - u;
+      const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
+      const bool owner = (ks == 0);
+      const int buf = seg & 1;
+      const uint32_t use = (uint32_t)(seg >> 1);
+      const int n_tile = tile % prm.tiles_n;
+      const int m_tile = 2 * (tile / prm.tiles_n) + (int)rank;
+      const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
+      const int yy = y0 + row / I5_TW, xx = x0 + row % I5_TW;
+      const bool valid = (m_tile < prm.tiles_m) && (yy < prm.H) && (xx < prm.W);
+      const int64_t p = (int64_t)yy * prm.W + xx;
+      const int n0 = n_tile * BN;
+
+      int npeer = 0;
+      const long long tw4 = tr_me ? clock64() : 0;
+      if (owner && ke < ipt) {
+        const long long tile_end = (long long)(tile + 1) * ipt;
+        long long c = pair + 1;
+        while (c < G && c * prm.total_units / G < tile_end) {
+          const unsigned int* f = prm.flags + 2 * c + rank;           // same-rank CTA of the later pair
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile const unsigned int*>(f) != prm.epoch) {
+              __nanosleep(64);
+              if (clock64() - t0 > 4000000000LL) {
+                printf("[smb] igemm_ph stream-K watchdog: CTA %d waiting for partial of CTA %d\n", (int)cta,
+                       (int)(2 * c + rank));
+                asm volatile("trap;");
+              }
+            }
+          }
+          __syncwarp();
+          (void)i5_ld_acquire(f);
+          ++npeer;
+          ++c;
+        }
+      }
+
+      const long long tw5 = tr_me ? clock64() : 0;
+      mbar_wait(&tmem_full_bar[buf], use & 1u, 66);
+      if (tr_me) {
+        w_flags += tw5 - tw4;
+        w_tfull += clock64() - tw5;
+      }
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
+      const uint32_t t_corr = t_main + (uint32_t)BN;
+      const bool staged = owner && prm.tma_out;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (staged && (c & 63) == 0) {
+          // the staging buffer is free once the previous group's tensor stores have read it
+          if (epi_leader) i5_bulk_wait_read0();
+          i5_epi_bar();
+        }
+        // Partial tiles travel through the workspace in a warp-coalesced layout: float4 number (c/4 + j) * 128 + row
+        // holds channels c+4j .. c+4j+3 of pixel `row` (a warp reads / writes 512 contiguous bytes per access).
+        // The first peer's partial is requested before the TMEM load so that the L2 round trip overlaps it.
+        float4 pv[8];
+        if (npeer > 0) {
+          const float4* src = reinterpret_cast<const float4*>(prm.ws + (size_t)(cta + 2) * I5_BM * BN) +
+                              (size_t)(c >> 2) * I5_BM + row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pv[j] = __ldcg(src + (size_t)j * I5_BM);
+        }
+        uint32_t rm[32], rc[32];
+        tmem_ld_32x32(t_main + (uint32_t)c, rm);
+        tmem_ld_32x32(t_corr + (uint32_t)c, rc);
+        tmem_ld_wait();
+        if (c + 32 >= BN) {                      // last TMEM read of this buffer: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);     // the leader's barrier collects 8 arrivals
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+        if (npeer > 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += pv[j].x; v[4 * j + 1] += pv[j].y; v[4 * j + 2] += pv[j].z; v[4 * j + 3] += pv[j].w;
+          }
+        }
+        for (int k = 2; k <= npeer; ++k) {       // fixed order => deterministic sums
+          const float4* src = reinterpret_cast<const float4*>(prm.ws + (size_t)(cta + 2 * k) * I5_BM * BN) +
+                              (size_t)(c >> 2) * I5_BM + row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldcg(src + (size_t)j * I5_BM);
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+          }
+        }
+        if (!owner) {
+          float4* dst = reinterpret_cast<float4*>(my_slot) + (size_t)(c >> 2) * I5_BM + row;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[(size_t)j * I5_BM] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (!staged) {
+          if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
+        } else {
+          epilogue_apply<32>(prm.ep, p, n0 + c, prm.N, v, valid);
+          if (prm.ep.out_f32 && valid) {
+            float4* dst = reinterpret_cast<float4*>(prm.ep.out_f32 + p * (int64_t)prm.N + n0 + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          // pixel `row` of the patch is 128-byte row `row` of the staging tile; 16-byte chunk index XOR (row & 7)
+          // = the SWIZZLE_128B pattern the tensor store expects (conflict free: 8 lanes cover 8 distinct chunks)
+          const uint32_t rbase = s_out + (uint32_t)row * 128u;
+          const uint32_t sw = (uint32_t)(row & 7);
+          const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 h, l;
+            split2_pack(v[8 * j], v[8 * j + 1], h.x, l.x);
+            split2_pack(v[8 * j + 2], v[8 * j + 3], h.y, l.y);
+            split2_pack(v[8 * j + 4], v[8 * j + 5], h.z, l.z);
+            split2_pack(v[8 * j + 6], v[8 * j + 7], h.w, l.w);
+            const uint32_t a = rbase + (((ch0 + (uint32_t)j) ^ sw) << 4);
+            i5_sts128(a, h);
+            i5_sts128(a + I5_OUT_PLANE, l);
+          }
+          if ((c & 63) == 32) {                  // 64-channel group complete: one tensor store per plane
+            fence_proxy_async_smem();
+            i5_epi_bar();
+            if (epi_leader) {
+              i5_tma_store_3d(&tmO_hi, sOut, n0 + (c & ~63), x0, y0);
+              i5_tma_store_3d(&tmO_lo, sOut + I5_OUT_PLANE, n0 + (c & ~63), x0, y0);
+              i5_bulk_commit();
+            }
+          }
+        }
+      }
+      if (!owner) {
+        // publish the partial tile: every epilogue thread's stores -> gpu scope, then one release store of the flag
+        __threadfence();
+        i5_epi_bar();
+        if (epi_leader) i5_st_release(prm.flags + cta, prm.epoch);
+      }
+      if (tr_me && seg == 0) tr[T5_CLK_EPI_FIRST] = (unsigned long long)clock64();
+      u += (ke - ks);
+    }
+    if (epi_leader) i5_bulk_wait0();             // all tensor stores of this CTA are complete before it exits
+    if (tr_me) {
+      tr[T5_CLK_EPI_END] = (unsigned long long)clock64();
+      tr[T5_W_FLAGS] = (unsigned long long)w_flags;
+      tr[T5_W_TMEM_FULL] = (unsigned long long)w_tfull;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  i5_cluster_sync();                         // the peer's shared memory / TMEM stay alive until both CTAs are done
+  if (warp == 1) i5_tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (tr && threadIdx.x == 0) {
+    tr[T5_CLK_OUT] = (unsigned long long)clock64();
+    tr[T5_GT_OUT] = i5_global_ns();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------------------
+int igemm_streamk_workspace(float** ws, unsigned int** flags, unsigned int* epoch);   // tc_igemm_v2.cu
+unsigned long long* get_igemm_trace();                                                // tc_igemm_v2.cu
+
+template <int BN>
+static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  using Cfg = I5Cfg<BN>;
+  IGemm5Params prm;
+  int rc = igemm_streamk_workspace(&prm.ws, &prm.flags, &prm.epoch);
+  if (rc) return rc;
+  prm.H = a.H;
+  prm.W = a.W;
+  prm.tiles_x = ceil_div(a.W, I5_TW);
+  prm.tiles_m = prm.tiles_x * ceil_div(a.H, I5_TH);
+  prm.tiles_n = b.N / BN;
+  prm.kchunks = b.K / 64;
+  prm.N = b.N;
+  const long long pair_tiles = (long long)ceil_div(prm.tiles_m, 2) * prm.tiles_n;
+  prm.total_units = pair_tiles * prm.kchunks;
+  prm.ep = ep;
+  // bf16 planes leave through shared memory + TMA; everything else (fp32 rows, masked copies, planar image gradient)
+  // keeps the per-thread stores
+  prm.tma_out = (ep.out_hi && ep.out_lo && !ep.outm_hi && !ep.out_planar3) ? 1 : 0;
+  static int no_tma_out = -1;
+  if (no_tma_out < 0) {
+    const char* e = getenv("SMB_PH_DIRECT_STORES");     // experiment knob: 1 = per-thread global stores as in igemm_tc2
+    no_tma_out = (e && atoi(e)) ? 1 : 0;
+  }
+  if (no_tma_out) prm.tma_out = 0;
+  prm.trace = get_igemm_trace();
+
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H};
+    const uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2};
+    const uint32_t box[3] = {64u, (uint32_t)I5_HW, (uint32_t)I5_HR};   // whole halo: 18 rows x 10 pixels x 64 channels
+    rc = make_tmap_bf16(&tmA_hi, a.hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmA_lo, a.lo, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)b.K, (uint64_t)b.N, (uint64_t)b.taps};
+    const uint64_t strides[2] = {(uint64_t)b.K * 2, (uint64_t)b.N * b.K * 2};
+    const uint32_t box[3] = {64u, (uint32_t)(BN / 2), 1u};
+    rc = make_tmap_bf16(&tmB_hi, b.hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmB_lo, b.lo, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (prm.tma_out) {
+    const uint64_t dims[3] = {(uint64_t)b.N, (uint64_t)a.W, (uint64_t)a.H};
+    const uint64_t strides[2] = {(uint64_t)b.N * 2, (uint64_t)a.W * b.N * 2};
+    const uint32_t box[3] = {64u, (uint32_t)I5_TW, (uint32_t)I5_TH};
+    rc = make_tmap_bf16(&tmO_hi, ep.out_hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmO_lo, ep.out_lo, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    tmO_hi = tmA_hi;      // never dereferenced
+    tmO_lo = tmA_lo;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMB_CUDA_CHECK(cudaFuncSetAttribute(igemm_ph_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SMB_CUDA_CHECK(cudaGetDevice(&dev));
+    SMB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (num_sms > 148) num_sms = 148;
+  }
+  const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units));
+  igemm_ph_kernel<BN><<<(unsigned)(2 * pairs), I5_THREADS, Cfg::SMEM, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi,
+                                                                           tmO_lo, prm);
+  SMB_LAUNCH_CHECK();
+  return SMB_OK;
+}
+
+int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+  SMB_REQUIRE(b.taps == 9, "igemm_ph: 3x3 convolutions only");
+  SMB_REQUIRE(a.C == b.K && b.K % 64 == 0 && b.N % 64 == 0, "igemm_ph: K=%d, N=%d must be multiples of 64", b.K, b.N);
+  if (a.pixels() == 0) return SMB_OK;
+  if (b.N % 128 == 0) return launch_igemm_ph_bn<128>(a, b, ep, st);
+  return launch_igemm_ph_bn<64>(a, b, ep, st);
+}
+
+}  // namespace smb

@@ -134,6 +134,8 @@ def _impl_from_env(name: str, default: int) -> int:
         return _abi.IMPL_TC_PAIR
     if v in ("halo", "tc_halo", "tc4", "4"):
         return _abi.IMPL_TC_HALO
+    if v in ("ph", "tc_ph", "tc5", "5"):
+        return _abi.IMPL_TC_PH
     if v in ("simt", "0"):
         return _abi.IMPL_SIMT
     raise ValueError(f"{name}={v!r}: expected 'tc' or 'simt'")
