@@ -69,13 +69,13 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 __device__ __forceinline__ float merge2(__nv_bfloat16 hi, __nv_bfloat16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);
 }
-// pack two floats' hi parts / lo parts into 32-bit words (element 0 in the low half)
+// pack two floats' hi parts / lo parts into 32-bit words (element 0 in the low half).  Same values as split2() on
+// each element (round-to-nearest-even both times), but with the packed two-element conversion: one F2FP per pair
+// instead of two F2F (the scalar conversion issues at a quarter of the rate and dominated the conv epilogues).
 __device__ __forceinline__ void split2_pack(float a, float b, uint32_t& hi2, uint32_t& lo2) {
-  __nv_bfloat16 ah, al, bh, bl;
-  split2(a, ah, al);
-  split2(b, bh, bl);
-  hi2 = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo2 = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(b), "f"(a));          // d.hi = first source, d.lo = second
+  const float ah = __uint_as_float(hi2 << 16), bh = __uint_as_float(hi2 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(b - bh), "f"(a - ah));
 }
 __device__ __forceinline__ float bf16lo_to_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_to_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

@@ -27,7 +27,8 @@
 namespace smb {
 using namespace tc;
 
-constexpr int I5_THREADS = 192;
+constexpr int I5_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int I5_EPI_THREADS = 256;
 constexpr int I5_BM = 128;                            // pixel rows per CTA (the pair covers 256)
 constexpr int I5_TH = 16, I5_TW = 8;                  // output patch of one CTA: 16 rows x 8 pixels
 constexpr int I5_HR = I5_TH + 2, I5_HW = I5_TW + 2;   // halo: 18 rows x 10 pixels
@@ -55,10 +56,12 @@ struct I5Cfg {
 
 struct IGemm5Params {
   int H, W, tiles_x, tiles_m, tiles_n, kchunks, N;
-  long long total_units;      // pair_tiles * kchunks
+  long long total_units;      // pair_tiles * kchunks * 9 work units (one tap of one K-chunk of one pair tile)
+  int align;                  // stream-K range boundaries are multiples of this many units: 9 (whole halo units) or 1
   float* ws;                  // [grid][128][BN] fp32 partial tiles (indexed by CTA id)
   unsigned int* flags;        // [grid]
   unsigned int epoch;
+  int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores
   unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
   Epilogue ep;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void i5_tma_store_3d(const CUtensorMap* m, const void
 __device__ __forceinline__ void i5_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void i5_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void i5_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void i5_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void i5_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void i5_tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
                "r"(ncols)
@@ -169,7 +172,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const uint32_t rank = i5_ctarank();                 // 0 = leader (issues the MMAs), 1 = peer
   const long long G = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const long long cta = blockIdx.x;
-  const long long u0 = pair * prm.total_units / G, u1 = (pair + 1) * prm.total_units / G;   // G <= total_units
+  // stream-K range of pair c: [bound(c), bound(c + 1)), boundaries aligned to prm.align units; G <= total / align
+  const long long n_al = prm.total_units / prm.align;
+  auto bound = [&](long long c) { return (c * n_al / G) * prm.align; };
+  const long long u0 = bound(pair), u1 = bound(pair + 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -185,7 +191,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ipt = prm.kchunks;                                // units per pair tile
+  const int ipt = prm.kchunks;                                // (K-chunk) halo loads per pair tile
+  const int tpt = 9 * ipt;                                    // work units (one tap of one K-chunk) per pair tile
   unsigned long long* tr = prm.trace ? prm.trace + (size_t)cta * 16 : nullptr;
   if (tr && threadIdx.x == 0) {
     unsigned int smid;
@@ -208,7 +215,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 8);      // 4 epilogue warps of each CTA
+      mbar_init(&tmem_empty_bar[s], 16);     // 8 epilogue warps of each CTA
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&b_full[s], 1);
@@ -229,29 +236,46 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own halo, own half of B) =====================
-    // Program order: A(u0); then per unit u: B taps 0..8 with A(u+1) issued after tap 2, so the next halo is in
-    // flight long before the tensor pipe needs it (it only needs the other A buffer to be drained).
+    // Program order: halo of the first unit; then one B tile per work unit (tap), with the NEXT unit's halo issued
+    // as soon as the other A buffer has been drained.  A range may start / end in the middle of a halo unit.
     if (elect_one()) {
       long long ga = 0, gb = 0, w_empty = 0;
-      auto issue_A = [&](long long u) {
+      // request the halo of unit u into the next A buffer; `force` = wait for the buffer, else give up if the MMAs of
+      // the unit that used it two units ago have not completed yet (the caller retries at the next tap)
+      auto issue_A = [&](long long u, bool force) -> bool {
         const int tile = (int)(u / ipt), kc = (int)(u % ipt);
         const int m_tile = 2 * (tile / prm.tiles_n) + (int)rank;
         const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
         const int abuf = (int)(ga & 1);
-        mbar_wait(&a_empty[abuf], (uint32_t)((ga >> 1) & 1) ^ 1u, 61);
+        const uint32_t par = (uint32_t)((ga >> 1) & 1) ^ 1u;
+        if (!mbar_try_wait(&a_empty[abuf], par)) {
+          if (!force) return false;
+          mbar_wait(&a_empty[abuf], par, 61);
+        }
         if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);      // bytes of both CTAs
         uint8_t* ah = sA + abuf * I5_A_BUF;
         i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
         i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
         ++ga;
+        return true;
       };
-      issue_A(u0);
-      for (long long u = u0; u < u1; ++u) {
-        const int tile = (int)(u / ipt), kc = (int)(u % ipt);
-        const int nb0 = (tile % prm.tiles_n) * BN + (int)rank * (BN / 2);
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++gb) {
-          if (tap == 3 && u + 1 < u1) issue_A(u + 1);
+      // halo units ((tile, K-chunk) pairs) touched by this range: u0/9 .. (u1-1)/9; the first and last may be partial
+      long long a_next = u0 / 9;
+      const long long a_last = (u1 - 1) / 9;
+      issue_A(a_next++, true);
+      for (long long w = u0; w < u1; ++w, ++gb) {
+        {
+          const long long u = w / 9;
+          const int tap = (int)(w % 9);
+          const int tile = (int)(u / ipt), kc = (int)(u % ipt);
+          const int nb0 = (tile % prm.tiles_n) * BN + (int)rank * (BN / 2);
+          // the next unit's halo goes out as soon as its buffer is free (checked at every tap, never blocking the B
+          // stream) and at the latest with this unit's last tap
+          if (prm.knob & 1) {
+            if (a_next == u + 1 && a_next <= a_last && issue_A(a_next, tap == 8)) ++a_next;
+          } else {
+            if (tap >= 3 && a_next == u + 1 && a_next <= a_last && issue_A(a_next, true)) ++a_next;
+          }
           const int bs = (int)(gb % NB);
           const long long tw0 = tr ? clock64() : 0;
           mbar_wait(&b_empty[bs], (uint32_t)((gb / NB) & 1) ^ 1u, 62);
@@ -274,9 +298,9 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       long long ga = 0, gb = 0, w_full = 0, w_tempty = 0;
       int seg = 0;
       for (long long u = u0; u < u1; ++seg) {
-        const int ks = (int)(u % ipt);
+        const int ks = (int)(u % tpt);
         const long long left = u1 - u;
-        const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
+        const int ke = (left < (long long)(tpt - ks)) ? ks + (int)left : tpt;
         const int buf = seg & 1;
         const uint32_t use = (uint32_t)(seg >> 1);
         const long long tw1 = tr ? clock64() : 0;
@@ -285,15 +309,20 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_fence_after();
         const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
         const uint32_t t_corr = t_main + (uint32_t)BN;
-        for (int kc = ks; kc < ke; ++kc, ++ga) {
-          const int abuf = (int)(ga & 1);
-          const long long tw2 = tr ? clock64() : 0;
-          mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
-          if (tr) w_full += clock64() - tw2;
-          const uint32_t a_hi = smem_u32(sA + abuf * I5_A_BUF);
-          const uint32_t a_lo = a_hi + I5_A_PLANE;
+        uint32_t a_hi = 0, a_lo = 0;
+        int abuf = 0;
+        {
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++gb) {
+          for (int t = ks; t < ke; ++t, ++gb) {
+            const int tap = t % 9;
+            if (t == ks || tap == 0) {             // first tap of a halo unit inside this range: its halo must have landed
+              abuf = (int)(ga & 1);
+              const long long tw2 = tr ? clock64() : 0;
+              mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
+              if (tr) w_full += clock64() - tw2;
+              a_hi = smem_u32(sA + abuf * I5_A_BUF);
+              a_lo = a_hi + I5_A_PLANE;
+            }
             const int bs = (int)(gb % NB);
             const long long tw3 = tr ? clock64() : 0;
             mbar_wait(&b_full[bs], (uint32_t)((gb / NB) & 1), 65);
@@ -312,14 +341,17 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               const uint64_t dal = i5_desc(a_lo + a_off + k * 32, I5_PITCH);
               const uint64_t dbh = i5_desc(b_hi + k * 32, 1024);
               const uint64_t dbl = i5_desc(b_lo + k * 32, 1024);
-              const uint32_t acc = (uint32_t)((kc > ks) || (tap > 0) || (k > 0));
+              const uint32_t acc = (uint32_t)((t > ks) || (k > 0));
               i5_umma(t_corr, dal, dbh, idesc, acc);
               i5_umma(t_corr, dah, dbl, idesc, 1u);
               i5_umma(t_main, dah, dbh, idesc, acc);
             }
             i5_commit_mc(&b_empty[bs]);          // frees this B stage in BOTH CTAs
+            if (tap == 8 || t == ke - 1) {       // last tap of this halo unit inside the range
+              i5_commit_mc(&a_empty[abuf]);      // frees this halo buffer in BOTH CTAs
+              ++ga;
+            }
           }
-          i5_commit_mc(&a_empty[abuf]);          // frees this halo buffer in BOTH CTAs
         }
         i5_commit_mc(&tmem_full_bar[buf]);       // accumulators complete, both CTAs
         u += (ke - ks);
@@ -332,8 +364,11 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else {
     // ===================== epilogue warps (each CTA drains its own 128 TMEM lanes) =====================
+    // warps 2-5 and 6-9 both cover the four TMEM lane quarters (quarter = warp % 4); set 0 takes the first 32
+    // channels of every 64-channel group, set 1 the second 32, and they meet at the staging buffer / named barrier
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int cset = (warp - 2) >> 2;
     const bool epi_leader = (warp == 2 && lane == 0);
     float* my_slot = prm.ws + (size_t)cta * I5_BM * BN;
     const uint32_t s_out = smem_u32(sOut);
@@ -341,10 +376,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const bool tr_me = tr && epi_leader;
     int seg = 0;
     for (long long u = u0; u < u1; ++seg) {
-      const int tile = (int)(u / ipt);
-      const int ks = (int)(u % ipt);
+      const int tile = (int)(u / tpt);
+      const int ks = (int)(u % tpt);
       const long long left = u1 - u;
-      const int ke = (left < (long long)(ipt - ks)) ? ks + (int)left : ipt;
+      const int ke = (left < (long long)(tpt - ks)) ? ks + (int)left : tpt;
       const bool owner = (ks == 0);
       const int buf = seg & 1;
       const uint32_t use = (uint32_t)(seg >> 1);
@@ -358,10 +393,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
       int npeer = 0;
       const long long tw4 = tr_me ? clock64() : 0;
-      if (owner && ke < ipt) {
-        const long long tile_end = (long long)(tile + 1) * ipt;
+      if (owner && ke < tpt) {
+        const long long tile_end = (long long)(tile + 1) * tpt;
         long long c = pair + 1;
-        while (c < G && c * prm.total_units / G < tile_end) {
+        while (c < G && bound(c) < tile_end) {
           const unsigned int* f = prm.flags + 2 * c + rank;           // same-rank CTA of the later pair
           if (lane == 0) {
             const long long t0 = clock64();
@@ -392,8 +427,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t t_corr = t_main + (uint32_t)BN;
       const bool staged = owner && prm.tma_out;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (staged && (c & 63) == 0) {
+      for (int c = cset * 32; c < BN; c += 64) {
+        if (staged) {
           // the staging buffer is free once the previous group's tensor stores have read it
           if (epi_leader) i5_bulk_wait_read0();
           i5_epi_bar();
@@ -412,10 +447,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tmem_ld_32x32(t_main + (uint32_t)c, rm);
         tmem_ld_32x32(t_corr + (uint32_t)c, rc);
         tmem_ld_wait();
-        if (c + 32 >= BN) {                      // last TMEM read of this buffer: hand it back to the MMA warp
+        if (c + 64 >= BN) {                      // this warp's last TMEM read of the buffer: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);     // the leader's barrier collects 8 arrivals
+          if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);     // the leader's barrier collects 16 arrivals
         }
         float v[32];
 #pragma unroll
@@ -465,7 +500,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             i5_sts128(a, h);
             i5_sts128(a + I5_OUT_PLANE, l);
           }
-          if ((c & 63) == 32) {                  // 64-channel group complete: one tensor store per plane
+          {                                      // 64-channel group complete: one tensor store per plane
             fence_proxy_async_smem();
             i5_epi_bar();
             if (epi_leader) {
@@ -522,7 +557,14 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   prm.kchunks = b.K / 64;
   prm.N = b.N;
   const long long pair_tiles = (long long)ceil_div(prm.tiles_m, 2) * prm.tiles_n;
-  prm.total_units = pair_tiles * prm.kchunks;
+  prm.total_units = pair_tiles * prm.kchunks * 9;
+  // Split at whole halo units (no halo is loaded twice, layers with one K-chunk get no partial tiles at all) unless
+  // that leaves the busiest pair more than 10 % above the mean (conv5_1: 160 units on 74 pairs = 3 vs 2.16).
+  {
+    const long long units = pair_tiles * prm.kchunks, g = std::min<long long>(74, units);
+    const double mean = (double)units / (double)g;
+    prm.align = ((double)((units + g - 1) / g) > 1.10 * mean) ? 1 : 9;
+  }
   prm.ep = ep;
   // bf16 planes leave through shared memory + TMA; everything else (fp32 rows, masked copies, planar image gradient)
   // keeps the per-thread stores
@@ -534,6 +576,12 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   }
   if (no_tma_out) prm.tma_out = 0;
   prm.trace = get_igemm_trace();
+  static int knob = -1;
+  if (knob < 0) {
+    const char* e = getenv("SMB_PH_KNOB");
+    knob = e ? atoi(e) : 0;
+  }
+  prm.knob = knob;
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo;
   {
@@ -578,7 +626,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     SMB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     if (num_sms > 148) num_sms = 148;
   }
-  const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units));
+  const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units / prm.align));
   igemm_ph_kernel<BN><<<(unsigned)(2 * pairs), I5_THREADS, Cfg::SMEM, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi,
                                                                            tmO_lo, prm);
   SMB_LAUNCH_CHECK();
