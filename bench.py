@@ -298,7 +298,7 @@ def run_ours(args):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {"kernel": "igemm_tc2_kernel (VGG conv forward + data-gradient launches)", "bound": "tensor",
+        roof = {"kernel": "igemm_ph_kernel (VGG conv forward + data-gradient launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms,
@@ -323,7 +323,7 @@ def run_ours(args):
         "dtype": "fp32 (tensor-core convs/Gram as 3x bf16 split products, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roof, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu, "with_cached_content_targets": cached,
-        "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "tc"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
+        "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "ph"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
     }
     return line
 

@@ -29,10 +29,10 @@ extern "C" {
 
 /* implementation selectors for smb_ctx_set_impl */
 #define SMB_IMPL_SIMT 0 /* fp32 CUDA-core cross-check kernels            */
-#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (default product; convs: persistent stream-K kernel) */
+#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (Gram default; convs: persistent stream-K kernel, second generation) */
 #define SMB_IMPL_TC_V1 2 /* convs only: first-generation tcgen05 kernel, one output tile per CTA             */
 #define SMB_IMPL_TC_HALO 4 /* convs only: 3x3 convs load the activation halo once per K-chunk and reuse it for all 9 taps */
-#define SMB_IMPL_TC_PH 5 /* convs only: CTA pair + activation halo + TMA-store epilogue for 3x3 convs, stream-K kernel otherwise */
+#define SMB_IMPL_TC_PH 5 /* convs only (DEFAULT): CTA pair + activation halo + TMA-store epilogue for 3x3 convs, stream-K kernel otherwise */
 #define SMB_IMPL_TC_PAIR 3 /* convs only: cta_group::2 CTA-pair kernel for N % 256 == 0, stream-K kernel otherwise */
 
 typedef struct smb_ctx smb_ctx;

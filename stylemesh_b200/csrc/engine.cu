@@ -147,7 +147,7 @@ using namespace smb;
 
 struct smb_ctx {
   Timing timing;
-  int conv_impl = IMPL_TC, gram_impl = IMPL_TC;
+  int conv_impl = IMPL_TC_PH, gram_impl = IMPL_TC;
   bool vgg_loaded = false;
   ConvLayer conv[SMB_NUM_VGG_CONVS];
   DeviceArena weights;

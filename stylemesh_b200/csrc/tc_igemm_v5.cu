@@ -61,7 +61,8 @@ struct IGemm5Params {
   float* ws;                  // [grid][128][BN] fp32 partial tiles (indexed by CTA id)
   unsigned int* flags;        // [grid]
   unsigned int epoch;
-  int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible
+  int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
+                              // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores
   unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
   Epilogue ep;
@@ -123,6 +124,38 @@ __device__ __forceinline__ void i5_umma(uint32_t tmem_d, uint64_t desc_a, uint64
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same MMA with the two shared-memory descriptors given as 32-bit halves (the high halves are compile-time constants,
+// the low halves differ by small immediates between the 12 MMAs of a tap)
+__device__ __forceinline__ void i5_umma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// walks halo units (pair tile, K-chunk) in stream-K order without divisions: unit = (pm * tiles_n + n_tile) * ipt + kc
+struct UnitWalk {
+  int kc, n_tile, pm;
+  __device__ __forceinline__ void init(int unit, int ipt, int tiles_n) {
+    kc = unit % ipt;
+    const int tile = unit / ipt;
+    n_tile = tile % tiles_n;
+    pm = tile / tiles_n;
+  }
+  __device__ __forceinline__ void next(int ipt, int tiles_n) {
+    if (++kc == ipt) {
+      kc = 0;
+      if (++n_tile == tiles_n) {
+        n_tile = 0;
+        ++pm;
+      }
+    }
+  }
+};
 // arrive (after all previously issued MMAs completed) on the barrier at this smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void i5_commit_mc(uint64_t* bar) {
   asm volatile(
@@ -237,53 +270,68 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own halo, own half of B) =====================
     // Program order: halo of the first unit; then one B tile per work unit (tap), with the NEXT unit's halo issued
-    // as soon as the other A buffer has been drained.  A range may start / end in the middle of a halo unit.
+    // at tap 3 of the current one (it only needs the other A buffer to be drained).  A range may start / end in the
+    // middle of a halo unit.  All indices are walked incrementally: this single thread has ~768 cycles per tap.
     if (elect_one()) {
-      long long ga = 0, gb = 0, w_empty = 0;
-      // request the halo of unit u into the next A buffer; `force` = wait for the buffer, else give up if the MMAs of
-      // the unit that used it two units ago have not completed yet (the caller retries at the next tap)
-      auto issue_A = [&](long long u, bool force) -> bool {
-        const int tile = (int)(u / ipt), kc = (int)(u % ipt);
-        const int m_tile = 2 * (tile / prm.tiles_n) + (int)rank;
-        const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
-        const int abuf = (int)(ga & 1);
+      const int w0 = (int)u0, w1 = (int)u1;
+      UnitWalk cur, nxt;
+      cur.init(w0 / 9, ipt, prm.tiles_n);
+      nxt = cur;
+      int tap = w0 % 9, u = w0 / 9, a_next = u;
+      const int a_last = (w1 - 1) / 9;
+      int ga = 0, bs = 0;
+      uint32_t bpar = 1;                       // parity of a never-completed phase: the first NB waits pass at once
+      long long w_empty = 0;
+      // request the halo of unit `nxt` into the next A buffer; `force` = wait for the buffer, else give up if the
+      // MMAs of the unit that used it two units ago have not completed yet (the caller retries at the next tap)
+      auto issue_A = [&](bool force) -> bool {
+        const int abuf = ga & 1;
         const uint32_t par = (uint32_t)((ga >> 1) & 1) ^ 1u;
         if (!mbar_try_wait(&a_empty[abuf], par)) {
           if (!force) return false;
           mbar_wait(&a_empty[abuf], par, 61);
         }
-        if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);      // bytes of both CTAs
-        uint8_t* ah = sA + abuf * I5_A_BUF;
-        i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
-        i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], kc * 64, x0 - 1, y0 - 1);
         ++ga;
+        if (prm.knob & 8) {
+          if (rank == 0) mbar_arrive(&a_full[abuf]);
+        } else {
+          const int m_tile = 2 * nxt.pm + (int)rank;
+          const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);      // bytes of both CTAs
+          uint8_t* ah = sA + abuf * I5_A_BUF;
+          i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
+          i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
+        }
+        nxt.next(ipt, prm.tiles_n);
+        ++a_next;
         return true;
       };
-      // halo units ((tile, K-chunk) pairs) touched by this range: u0/9 .. (u1-1)/9; the first and last may be partial
-      long long a_next = u0 / 9;
-      const long long a_last = (u1 - 1) / 9;
-      issue_A(a_next++, true);
-      for (long long w = u0; w < u1; ++w, ++gb) {
-        {
-          const long long u = w / 9;
-          const int tap = (int)(w % 9);
-          const int tile = (int)(u / ipt), kc = (int)(u % ipt);
-          const int nb0 = (tile % prm.tiles_n) * BN + (int)rank * (BN / 2);
-          // the next unit's halo goes out as soon as its buffer is free (checked at every tap, never blocking the B
-          // stream) and at the latest with this unit's last tap
-          if (prm.knob & 1) {
-            if (a_next == u + 1 && a_next <= a_last && issue_A(a_next, tap == 8)) ++a_next;
-          } else {
-            if (tap >= 3 && a_next == u + 1 && a_next <= a_last && issue_A(a_next, true)) ++a_next;
-          }
-          const int bs = (int)(gb % NB);
-          const long long tw0 = tr ? clock64() : 0;
-          mbar_wait(&b_empty[bs], (uint32_t)((gb / NB) & 1) ^ 1u, 62);
-          if (tr) w_empty += clock64() - tw0;
+      issue_A(true);
+      for (int w = w0; w < w1; ++w) {
+        if (a_next == u + 1 && a_next <= a_last) {
+          if (prm.knob & 1) issue_A(tap == 8);
+          else if (tap >= 3) issue_A(true);
+        }
+        const long long tw0 = tr ? clock64() : 0;
+        mbar_wait(&b_empty[bs], bpar, 62);
+        if (tr) w_empty += clock64() - tw0;
+        if (prm.knob & 8) {
+          if (rank == 0) mbar_arrive(&b_full[bs]);
+        } else {
           if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_STAGE);
           uint8_t* bh = sB + bs * Cfg::B_STAGE;
-          i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], kc * 64, nb0, tap);
-          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], kc * 64, nb0, tap);
+          const int nb0 = cur.n_tile * BN + (int)rank * (BN / 2);
+          i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], cur.kc * 64, nb0, tap);
+          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], cur.kc * 64, nb0, tap);
+        }
+        if (++bs == NB) {
+          bs = 0;
+          bpar ^= 1u;
+        }
+        if (++tap == 9) {
+          tap = 0;
+          ++u;
+          cur.next(ipt, prm.tiles_n);
         }
       }
       if (tr) {
@@ -293,14 +341,26 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // One thread issues 12 MMAs per tap (768 tensor cycles at N = 128): the scalar work per tap has to stay well
+    // below that, so descriptors are built from precomputed 32-bit halves (low word = address >> 4 | LBO, one add per
+    // operand) and every index is a wrapped counter.
     if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * I5_BM, BN, 0, 0);
-      long long ga = 0, gb = 0, w_full = 0, w_tempty = 0;
-      int seg = 0;
-      for (long long u = u0; u < u1; ++seg) {
-        const int ks = (int)(u % tpt);
-        const long long left = u1 - u;
-        const int ke = (left < (long long)(tpt - ks)) ? ks + (int)left : tpt;
+      constexpr uint32_t HI_A = (uint32_t)(I5_PITCH >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+      constexpr uint32_t HI_B = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t A_LO_PLANE = I5_A_PLANE >> 4, B_LO_PLANE = Cfg::B_PLANE >> 4;
+      const uint32_t a_word0 = (smem_u32(sA) >> 4) | (1u << 16);                      // low descriptor word of A buffer 0 (hi plane)
+      const uint32_t b_word0 = (smem_u32(sB) >> 4) | (1u << 16);                      // ... of B stage 0 (hi plane)
+      const int w1 = (int)u1;
+      int w = (int)u0;
+      int tap = w % 9, ga = 0, bs = 0, seg = 0;
+      uint32_t bfpar = 0, a_word = 0;
+      int abuf = 0;
+      long long w_full = 0, w_tempty = 0;
+      bool first = true;
+      while (w < w1) {
+        const int ks = w % tpt;
+        const int ke = (w1 - w < tpt - ks) ? ks + (w1 - w) : tpt;
         const int buf = seg & 1;
         const uint32_t use = (uint32_t)(seg >> 1);
         const long long tw1 = tr ? clock64() : 0;
@@ -309,52 +369,50 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_fence_after();
         const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
         const uint32_t t_corr = t_main + (uint32_t)BN;
-        uint32_t a_hi = 0, a_lo = 0;
-        int abuf = 0;
-        {
 #pragma unroll 1
-          for (int t = ks; t < ke; ++t, ++gb) {
-            const int tap = t % 9;
-            if (t == ks || tap == 0) {             // first tap of a halo unit inside this range: its halo must have landed
-              abuf = (int)(ga & 1);
-              const long long tw2 = tr ? clock64() : 0;
-              mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
-              if (tr) w_full += clock64() - tw2;
-              a_hi = smem_u32(sA + abuf * I5_A_BUF);
-              a_lo = a_hi + I5_A_PLANE;
-            }
-            const int bs = (int)(gb % NB);
-            const long long tw3 = tr ? clock64() : 0;
-            mbar_wait(&b_full[bs], (uint32_t)((gb / NB) & 1), 65);
-            if (tr) {
-              const long long now = clock64();
-              w_full += now - tw3;
-              if (gb == 0) tr[T5_CLK_MMA_FIRST] = (unsigned long long)now;
-            }
-            tc_fence_after();
-            const uint32_t a_off = (uint32_t)((tap / 3) * I5_PITCH + (tap % 3) * 128);   // halo coords of the tap
-            const uint32_t b_hi = smem_u32(sB + bs * Cfg::B_STAGE);
-            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+        for (int t = ks; t < ke; ++t) {
+          if (t == ks || tap == 0) {             // first tap of a halo unit inside this range: its halo must have landed
+            abuf = ga & 1;
+            const long long tw2 = tr ? clock64() : 0;
+            mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
+            if (tr) w_full += clock64() - tw2;
+            a_word = a_word0 + (uint32_t)abuf * (uint32_t)(I5_A_BUF >> 4);
+          }
+          const long long tw3 = tr ? clock64() : 0;
+          mbar_wait(&b_full[bs], bfpar, 65);
+          if (tr) {
+            const long long now = clock64();
+            w_full += now - tw3;
+            if (first) tr[T5_CLK_MMA_FIRST] = (unsigned long long)now;
+            first = false;
+          }
+          tc_fence_after();
+          const int dy = (tap >= 6) ? 2 : (tap >= 3 ? 1 : 0);
+          const uint32_t a_t = a_word + (uint32_t)(dy * (I5_PITCH >> 4) + (tap - 3 * dy) * 8);   // halo coords of the tap
+          const uint32_t b_t = b_word0 + (uint32_t)bs * (uint32_t)(Cfg::B_STAGE >> 4);
+          if (!(prm.knob & 4)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t dah = i5_desc(a_hi + a_off + k * 32, I5_PITCH);
-              const uint64_t dal = i5_desc(a_lo + a_off + k * 32, I5_PITCH);
-              const uint64_t dbh = i5_desc(b_hi + k * 32, 1024);
-              const uint64_t dbl = i5_desc(b_lo + k * 32, 1024);
               const uint32_t acc = (uint32_t)((t > ks) || (k > 0));
-              i5_umma(t_corr, dal, dbh, idesc, acc);
-              i5_umma(t_corr, dah, dbl, idesc, 1u);
-              i5_umma(t_main, dah, dbh, idesc, acc);
-            }
-            i5_commit_mc(&b_empty[bs]);          // frees this B stage in BOTH CTAs
-            if (tap == 8 || t == ke - 1) {       // last tap of this halo unit inside the range
-              i5_commit_mc(&a_empty[abuf]);      // frees this halo buffer in BOTH CTAs
-              ++ga;
+              i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+              i5_umma2(t_corr, a_t + 2 * k, HI_A, b_t + B_LO_PLANE + 2 * k, HI_B, idesc, 1u);
+              i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
             }
           }
+          i5_commit_mc(&b_empty[bs]);            // frees this B stage in BOTH CTAs
+          if (++bs == NB) {
+            bs = 0;
+            bfpar ^= 1u;
+          }
+          if (tap == 8 || t == ke - 1) {         // last tap of this halo unit inside the range
+            i5_commit_mc(&a_empty[abuf]);        // frees this halo buffer in BOTH CTAs
+            ++ga;
+          }
+          if (++tap == 9) tap = 0;
         }
         i5_commit_mc(&tmem_full_bar[buf]);       // accumulators complete, both CTAs
-        u += (ke - ks);
+        w += (ke - ks);
+        ++seg;
       }
       if (tr) {
         tr[T5_CLK_MMA_END] = (unsigned long long)clock64();
@@ -452,6 +510,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);     // the leader's barrier collects 16 arrivals
         }
+        if ((prm.knob & 2) && owner) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
@@ -636,6 +695,8 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
 int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
   SMB_REQUIRE(b.taps == 9, "igemm_ph: 3x3 convolutions only");
   SMB_REQUIRE(a.C == b.K && b.K % 64 == 0 && b.N % 64 == 0, "igemm_ph: K=%d, N=%d must be multiples of 64", b.K, b.N);
+  SMB_REQUIRE((long long)ceil_div(a.W, I5_TW) * ceil_div(a.H, I5_TH) * (b.N / 64) * (b.K / 64) * 9 < (1LL << 30),
+              "igemm_ph: problem too large for 32-bit work indices");
   if (a.pixels() == 0) return SMB_OK;
   if (b.N % 128 == 0) return launch_igemm_ph_bn<128>(a, b, ep, st);
   return launch_igemm_ph_bn<64>(a, b, ep, st);

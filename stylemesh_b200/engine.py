@@ -154,7 +154,7 @@ class VGGEngine:
         self._ctx = self._lib.smb_ctx_create()
         if not self._ctx:
             raise _abi.StyleMeshB200Error(f"smb_ctx_create failed: {_abi.last_error()}")
-        self.conv_impl = _impl_from_env("SMB_CONV_IMPL", _abi.IMPL_TC) if conv_impl is None else conv_impl
+        self.conv_impl = _impl_from_env("SMB_CONV_IMPL", _abi.IMPL_TC_PH) if conv_impl is None else conv_impl
         self.gram_impl = _impl_from_env("SMB_GRAM_IMPL", _abi.IMPL_TC) if gram_impl is None else gram_impl
         _abi.check(self._lib.smb_ctx_set_impl(self._ctx, self.conv_impl, self.gram_impl), "smb_ctx_set_impl")
         ws, bs = [], []

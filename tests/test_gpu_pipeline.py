@@ -57,8 +57,9 @@ def assert_texels(got, want, what=""):
 
 
 def make_pipeline(spec, tmp_path, impl):
-    # SMB_TEST_TC_VARIANT=pair|tc1 re-runs the "tc" cases on another tcgen05 conv kernel generation
-    os.environ["SMB_CONV_IMPL"] = os.environ.get("SMB_TEST_TC_VARIANT", "tc") if impl == "tc" else impl
+    # "tc" = the product default (pair + halo conv kernel); SMB_TEST_TC_VARIANT=tc|pair|halo|tc1 re-runs these cases on
+    # another tcgen05 conv kernel generation
+    os.environ["SMB_CONV_IMPL"] = os.environ.get("SMB_TEST_TC_VARIANT", "ph") if impl == "tc" else impl
     os.environ["SMB_GRAM_IMPL"] = impl
     from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline
     preset, sd, layers, view, style, hierarchical = build_inputs(spec)

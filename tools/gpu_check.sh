@@ -16,7 +16,7 @@ run() {  # name, pytest args...
 run texture tests/test_gpu_texture.py
 run units_simt tests/test_gpu_vgg_units.py -k "simt or maxpool"
 run units_tc1 tests/test_gpu_vgg_units.py -k "tc1"
-run units_tc tests/test_gpu_vgg_units.py -k "tc and not tc1"
+run units_tc tests/test_gpu_vgg_units.py -k "(tc or pair or halo or ph) and not tc1"
 run pipeline_simt tests/test_gpu_pipeline.py -k "simt"
 run pipeline_tc tests/test_gpu_pipeline.py -k "not simt"
 run fullsize tests/test_gpu_fullsize_properties.py
