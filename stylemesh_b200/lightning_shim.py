@@ -143,6 +143,15 @@ class Trainer:
         if self.world_size > 1 and not dist.is_initialized():
             dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
 
+    def _my_batches(self, loader):
+        """(batch_idx, batch) of this rank: view sharding, rank r owns views r, r+N, ..."""
+        for batch_idx, batch in enumerate(loader):
+            if 0 <= self.limit_train_batches <= batch_idx:
+                break
+            if batch_idx % self.world_size != self.rank:
+                continue
+            yield batch_idx, batch
+
     def fit(self, model: LightningModule, datamodule: LightningDataModule):
         if not torch.cuda.is_available():
             raise RuntimeError("stylemesh_b200 Trainer needs a CUDA device (no CPU path)")
@@ -156,20 +165,27 @@ class Trainer:
         (optimizer,), schedulers = model.configure_optimizers()
         train_loader = datamodule.train_dataloader()
         val_loader = datamodule.val_dataloader()
+        from .staging import BatchStager
+        stager = BatchStager(device)
         for epoch in range(self.max_epochs):
             model.current_epoch = epoch
             model.on_train_epoch_start()
             model.train()
-            for batch_idx, batch in enumerate(train_loader):
-                if 0 <= self.limit_train_batches <= batch_idx:
-                    break
-                if batch_idx % self.world_size != self.rank:      # view sharding: rank r owns views r, r+N, ...
-                    continue
-                batch = _to_device(batch, device)
+            # the H2D copy of the NEXT view is issued on a copy stream before this view's kernels are launched
+            # (stylemesh_b200/staging.py); Lightning's own loop copies on the compute stream right before the step
+            mine = self._my_batches(train_loader)
+            nxt = next(mine, None)
+            ticket = stager.stage(nxt[1]) if nxt is not None else None
+            while nxt is not None:
+                batch_idx, cur_ticket = nxt[0], ticket
+                nxt = next(mine, None)
+                ticket = stager.stage(nxt[1]) if nxt is not None else None
+                batch = stager.acquire(cur_ticket)
                 optimizer.zero_grad()
                 out = model.training_step(batch, batch_idx)
                 out["loss"].backward()
                 optimizer.step()
+                stager.release(cur_ticket)
                 self.global_step += 1
             model.on_train_epoch_end()
             if val_loader is not None:

@@ -110,7 +110,7 @@ class SyntheticView:
                              pm(self.mask), pm(self.angle_guidance), pm(self.angle_degrees), self.index)
 
     def h2d_bytes(self) -> int:
-        ts = [self.rgb, self.depth_level, self.rounded_depth_level, self.other_depth_level, self.interp_weight,
+        ts = [self.rgb, self.depth, self.depth_level, self.rounded_depth_level, self.other_depth_level, self.interp_weight,
               self.mask, self.angle_guidance, self.angle_degrees] + list(self.uvs)
         return int(sum(t.numel() * t.element_size() for t in ts))
 

@@ -126,3 +126,24 @@ def test_module_autograd_surface_on_fake_engine(monkeypatch, tmp_path):
     (1e-4 * os_ + 70 * oc_).backward()
     assert rel(float(s), float(os_)) < 1e-4 and rel(float(c), float(oc_)) < 1e-4
     assert (p1.grad - p2.grad).norm() <= 1e-4 * p2.grad.norm()
+
+
+def test_packed_batch_round_trip():
+    """staging.PackedBatch: the collated byte buffer reproduces every tensor of the 13-tuple (dtype, shape, bytes),
+    the dataset index stays a host tensor, offsets are 256-byte aligned."""
+    from stylemesh_b200 import staging, synthetic as syn
+    v = syn.make_view(1003, (32, 48), [(32, 48), (48, 64)])
+    batch = v.as_batch()
+    p = staging.PackedBatch(batch, pin=False)
+    assert p.nbytes % 256 == 0 and p.payload_bytes == v.h2d_bytes() + 2 * 16 * 4      # + the two 4x4 camera matrices
+    back = p.views_of(p.host.clone())
+    assert isinstance(back, tuple) and len(back) == 13 and isinstance(back[9], list)
+    assert back[8] is batch[8]
+    flat_a, flat_b = [], []
+    staging._flatten(batch, flat_a, [])
+    staging._flatten(back, flat_b, [])
+    assert len(flat_a) == len(flat_b) == 14
+    for a, b in zip(flat_a, flat_b):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    for m in p.meta:
+        assert m is None or m[0] % 256 == 0
