@@ -196,7 +196,8 @@ static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& ou
 }
 
 static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  if (impl == IMPL_TC_PH) return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_ph(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
+  if (impl == IMPL_TC_PH)
+    return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_HALO) return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_halo(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_PAIR) return (b.N % 128 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
@@ -688,7 +689,7 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
     if (ctx->conv_impl != IMPL_SIMT && ctx->conv_impl != IMPL_TC_V1) {
       Epilogue ep;                          // tcgen05 implicit GEMM with N padded 3 -> 16, planar fp32 output
       ep.out_planar3 = d_image;
-      rc = launch_igemm_tc2(s.dz[0], ctx->conv[0].dgrad, ep, st);
+      rc = igemm(ctx->conv_impl, s.dz[0], ctx->conv[0].dgrad, ep, st);
     } else {
       rc = launch_conv_first_dgrad(s.dz[0], ctx->conv[0].w_oihw, kCout[0], d_image, st);
     }

@@ -166,8 +166,8 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // bf16 tensor, `rank` dims (dim 0 innermost/contiguous), SWIZZLE_128B, zero fill out of bounds.
-inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes /* rank-1 entries, for dims 1.. */, const uint32_t* box) {
+inline int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes /* rank-1 entries, for dims 1.. */, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -182,7 +182,7 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+  CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -192,6 +192,15 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     return SMB_ERR_CUDA;
   }
   return SMB_OK;
+}
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+// fp32 tensor, same conventions (a 32-element inner box is one 128-byte swizzle row)
+inline int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_typed(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace tc

@@ -48,9 +48,10 @@ struct I5Cfg {
   static constexpr int B_PLANE = (BN / 2) * 128;                 // this CTA's half of the B tile of one tap
   static constexpr int B_STAGE = 2 * B_PLANE;                    // hi + lo
   static constexpr int NB_FIT = (I5_SMEM_LIMIT - 1024 - 2 * I5_A_BUF - I5_OUT_BYTES - I5_BAR_BYTES) / B_STAGE;
+  static constexpr int TMEM_NEED = 2 * 2 * BN;                          // 2 tile buffers x (main + corr)
   static constexpr int NB = NB_FIT < I5_MAX_NB ? NB_FIT : I5_MAX_NB;
   static constexpr int SMEM = 1024 + 2 * I5_A_BUF + I5_OUT_BYTES + NB * B_STAGE + I5_BAR_BYTES;
-  static constexpr int TMEM_COLS = (2 * 2 * BN) <= 256 ? 256 : 512;   // 2 tile buffers x (main + corr)
+  static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 256 ? 256 : 512);
   static_assert(NB >= 4, "B ring too shallow");
 };
 
@@ -63,7 +64,7 @@ struct IGemm5Params {
   unsigned int epoch;
   int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
-  int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores
+  int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do
   unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
   Epilogue ep;
 };
@@ -484,6 +485,47 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
       const uint32_t t_corr = t_main + (uint32_t)BN;
       const bool staged = owner && prm.tma_out;
+      if constexpr (BN == 16) {
+        // narrow tile (data gradient of the 3-channel first layer, N padded 3 -> 16): main and corr are adjacent
+        // 16-column blocks, one 32-column TMEM load fetches both; only warp set 0 computes, set 1 just keeps the
+        // barrier counts
+        float v[16];
+        if (cset == 0) {
+          uint32_t rm[32];
+          tmem_ld_32x32(t_main, rm);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rm[16 + j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);
+        if (cset == 0) {
+          for (int k = 1; k <= npeer; ++k) {
+            const float4* src = reinterpret_cast<const float4*>(prm.ws + (size_t)(cta + 2 * k) * I5_BM * BN) + row;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 a = __ldcg(src + (size_t)j * I5_BM);
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
+          }
+          if (!owner) {
+            float4* dst = reinterpret_cast<float4*>(my_slot) + row;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[(size_t)j * I5_BM] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if (valid) {
+            if (prm.ep.out_planar3) {            // (3, H, W) fp32 image gradient
+              const int64_t P = (int64_t)prm.H * prm.W;
+              prm.ep.out_planar3[p] = v[0];
+              prm.ep.out_planar3[P + p] = v[1];
+              prm.ep.out_planar3[2 * P + p] = v[2];
+            } else {
+              epilogue_store<16>(prm.ep, p, n0, prm.N, v);
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = cset * 32; c < BN; c += 64) {
         if (staged) {
@@ -538,15 +580,29 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
         } else {
           epilogue_apply<32>(prm.ep, p, n0 + c, prm.N, v, valid);
-          if (prm.ep.out_f32 && valid) {
-            float4* dst = reinterpret_cast<float4*>(prm.ep.out_f32 + p * (int64_t)prm.N + n0 + c);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
           // pixel `row` of the patch is 128-byte row `row` of the staging tile; 16-byte chunk index XOR (row & 7)
           // = the SWIZZLE_128B pattern the tensor store expects (conflict free: 8 lanes cover 8 distinct chunks)
           const uint32_t rbase = s_out + (uint32_t)row * 128u;
           const uint32_t sw = (uint32_t)(row & 7);
+          if (prm.tma_out == 2) {
+            // fp32 rows: this warp set's 32 channels are one 128-byte row of ITS half of the staging buffer
+            const uint32_t hb = rbase + (uint32_t)cset * I5_OUT_PLANE;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 w4;
+              w4.x = __float_as_uint(v[4 * j]); w4.y = __float_as_uint(v[4 * j + 1]);
+              w4.z = __float_as_uint(v[4 * j + 2]); w4.w = __float_as_uint(v[4 * j + 3]);
+              i5_sts128(hb + ((((uint32_t)j) ^ sw) << 4), w4);
+            }
+            fence_proxy_async_smem();
+            i5_epi_bar();
+            if (epi_leader) {
+              i5_tma_store_3d(&tmO_hi, sOut, n0 + (c & ~63), x0, y0);
+              i5_tma_store_3d(&tmO_hi, sOut + I5_OUT_PLANE, n0 + (c & ~63) + 32, x0, y0);
+              i5_bulk_commit();
+            }
+            continue;
+          }
           const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -570,6 +626,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           }
         }
       }
+      }
       if (!owner) {
         // publish the partial tile: every epilogue thread's stores -> gpu scope, then one release store of the flag
         __threadfence();
@@ -579,7 +636,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (tr_me && seg == 0) tr[T5_CLK_EPI_FIRST] = (unsigned long long)clock64();
       u += (ke - ks);
     }
-    if (epi_leader) i5_bulk_wait0();             // all tensor stores of this CTA are complete before it exits
+    // shared memory may go once the tensor stores have READ it; their global writes complete with the grid
+    if (epi_leader) i5_bulk_wait_read0();
     if (tr_me) {
       tr[T5_CLK_EPI_END] = (unsigned long long)clock64();
       tr[T5_W_FLAGS] = (unsigned long long)w_flags;
@@ -627,7 +685,11 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   prm.ep = ep;
   // bf16 planes leave through shared memory + TMA; everything else (fp32 rows, masked copies, planar image gradient)
   // keeps the per-thread stores
-  prm.tma_out = (ep.out_hi && ep.out_lo && !ep.outm_hi && !ep.out_planar3) ? 1 : 0;
+  prm.tma_out = 0;
+  if (BN >= 64 && !ep.outm_hi && !ep.out_planar3) {
+    if (ep.out_hi && ep.out_lo && !ep.out_f32) prm.tma_out = 1;
+    else if (ep.out_f32 && !ep.out_hi) prm.tma_out = 2;
+  }
   static int no_tma_out = -1;
   if (no_tma_out < 0) {
     const char* e = getenv("SMB_PH_DIRECT_STORES");     // experiment knob: 1 = per-thread global stores as in igemm_tc2
@@ -661,7 +723,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     rc = make_tmap_bf16(&tmB_lo, b.lo, 3, dims, strides, box);
     if (rc) return rc;
   }
-  if (prm.tma_out) {
+  if (prm.tma_out == 1) {
     const uint64_t dims[3] = {(uint64_t)b.N, (uint64_t)a.W, (uint64_t)a.H};
     const uint64_t strides[2] = {(uint64_t)b.N * 2, (uint64_t)a.W * b.N * 2};
     const uint32_t box[3] = {64u, (uint32_t)I5_TW, (uint32_t)I5_TH};
@@ -669,6 +731,13 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     if (rc) return rc;
     rc = make_tmap_bf16(&tmO_lo, ep.out_lo, 3, dims, strides, box);
     if (rc) return rc;
+  } else if (prm.tma_out == 2) {
+    const uint64_t dims[3] = {(uint64_t)b.N, (uint64_t)a.W, (uint64_t)a.H};
+    const uint64_t strides[2] = {(uint64_t)b.N * 4, (uint64_t)a.W * b.N * 4};
+    const uint32_t box[3] = {32u, (uint32_t)I5_TW, (uint32_t)I5_TH};          // 32 fp32 channels = one 128-byte row
+    rc = make_tmap_f32(&tmO_hi, ep.out_f32, 3, dims, strides, box);
+    if (rc) return rc;
+    tmO_lo = tmO_hi;
   } else {
     tmO_hi = tmA_hi;      // never dereferenced
     tmO_lo = tmA_lo;
@@ -694,10 +763,12 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
 
 int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
   SMB_REQUIRE(b.taps == 9, "igemm_ph: 3x3 convolutions only");
-  SMB_REQUIRE(a.C == b.K && b.K % 64 == 0 && b.N % 64 == 0, "igemm_ph: K=%d, N=%d must be multiples of 64", b.K, b.N);
-  SMB_REQUIRE((long long)ceil_div(a.W, I5_TW) * ceil_div(a.H, I5_TH) * (b.N / 64) * (b.K / 64) * 9 < (1LL << 30),
+  SMB_REQUIRE(a.C == b.K && b.K % 64 == 0 && (b.N % 64 == 0 || b.N == 16),
+              "igemm_ph: K=%d must be a multiple of 64, N=%d a multiple of 64 (or the padded 16)", b.K, b.N);
+  SMB_REQUIRE((long long)ceil_div(a.W, I5_TW) * ceil_div(a.H, I5_TH) * ceil_div(b.N, 64) * (b.K / 64) * 9 < (1LL << 30),
               "igemm_ph: problem too large for 32-bit work indices");
   if (a.pixels() == 0) return SMB_OK;
+  if (b.N == 16) return launch_igemm_ph_bn<16>(a, b, ep, st);
   if (b.N % 128 == 0) return launch_igemm_ph_bn<128>(a, b, ep, st);
   return launch_igemm_ph_bn<64>(a, b, ep, st);
 }
