@@ -40,7 +40,7 @@ constexpr int I5_OUT_PLANE = I5_BM * 128;             // 128 pixels x 64 channel
 constexpr int I5_OUT_BYTES = 2 * I5_OUT_PLANE;        // hi + lo staging of one 64-channel group
 constexpr int I5_BAR_BYTES = 512;
 constexpr int I5_SMEM_LIMIT = 227 * 1024;
-constexpr int I5_MAX_NB = 8;
+constexpr int I5_MAX_NB = 9;                          // 9 stages hold all taps of a 64-wide layer (resident B)
 constexpr uint32_t I5_PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address -> same offset in CTA 0 of the pair
 
 template <int BN>
@@ -62,6 +62,7 @@ struct IGemm5Params {
   float* ws;                  // [grid][128][BN] fp32 partial tiles (indexed by CTA id)
   unsigned int* flags;        // [grid]
   unsigned int epoch;
+  int resident;               // 1: one K-chunk, one N tile -> the 9 B tiles are loaded once and stay in stages 0..8
   int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do
@@ -308,7 +309,23 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         return true;
       };
       issue_A(true);
-      for (int w = w0; w < w1; ++w) {
+      if (prm.resident) {
+        // every tile of this layer multiplies the same nine B tiles (all CTAs would otherwise stream the same 144 KB
+        // from a handful of L2 lines): load them once, then only halos move
+        for (int t9 = 0; t9 < 9; ++t9) {
+          if (prm.knob & 8) {
+            if (rank == 0) mbar_arrive(&b_full[t9]);
+            continue;
+          }
+          if (rank == 0) mbar_arrive_expect_tx(&b_full[t9], 2 * Cfg::B_STAGE);
+          uint8_t* bh = sB + t9 * Cfg::B_STAGE;
+          const int nb0 = (int)rank * (BN / 2);
+          i5_tma_load_3d(bh, &tmB_hi, &b_full[t9], 0, nb0, t9);
+          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[t9], 0, nb0, t9);
+        }
+        while (a_next <= a_last) issue_A(true);
+      }
+      for (int w = prm.resident ? w1 : w0; w < w1; ++w) {
         if (a_next == u + 1 && a_next <= a_last) {
           if (prm.knob & 1) issue_A(tap == 8);
           else if (tap >= 3) issue_A(true);
@@ -379,6 +396,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (tr) w_full += clock64() - tw2;
             a_word = a_word0 + (uint32_t)abuf * (uint32_t)(I5_A_BUF >> 4);
           }
+          if (prm.resident) {                    // stage = tap, loaded once (phase 0 stays complete)
+            bs = tap;
+            bfpar = 0;
+          }
           const long long tw3 = tr ? clock64() : 0;
           mbar_wait(&b_full[bs], bfpar, 65);
           if (tr) {
@@ -400,10 +421,12 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
             }
           }
-          i5_commit_mc(&b_empty[bs]);            // frees this B stage in BOTH CTAs
-          if (++bs == NB) {
-            bs = 0;
-            bfpar ^= 1u;
+          if (!prm.resident) {
+            i5_commit_mc(&b_empty[bs]);          // frees this B stage in BOTH CTAs
+            if (++bs == NB) {
+              bs = 0;
+              bfpar ^= 1u;
+            }
           }
           if (tap == 8 || t == ke - 1) {         // last tap of this halo unit inside the range
             i5_commit_mc(&a_empty[abuf]);        // frees this halo buffer in BOTH CTAs
@@ -696,6 +719,15 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     no_tma_out = (e && atoi(e)) ? 1 : 0;
   }
   if (no_tma_out) prm.tma_out = 0;
+  prm.resident = (prm.kchunks == 1 && prm.tiles_n == 1 && Cfg::NB >= 9) ? 1 : 0;
+  {
+    static int no_resident = -1;
+    if (no_resident < 0) {
+      const char* e = getenv("SMB_PH_NO_RESIDENT");     // experiment knob
+      no_resident = (e && atoi(e)) ? 1 : 0;
+    }
+    if (no_resident) prm.resident = 0;
+  }
   prm.trace = get_igemm_trace();
   static int knob = -1;
   if (knob < 0) {
