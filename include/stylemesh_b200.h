@@ -107,7 +107,8 @@ int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc
 /* Free every slot's device memory (e.g. after the one-off style-target pass over large style images). */
 int smb_ctx_release_slots(smb_ctx* ctx);
 
-/* Masked Gram of relu(conv_i):  G = inv_n * sum_p m_p F_p F_p^T  -> gram_out (C x C fp32). rowmask may be NULL. */
+/* Masked Gram of relu(conv_i):  G = inv_n * sum_p m_p F_p F_p^T  -> gram_out (C x C fp32). rowmask: one float per
+ * pixel, exactly 0 or 1 (the reference compacts features by `mask > 0`, cs:136-143), or NULL for all ones. */
 int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, float* gram_out,
                    void* stream);
 

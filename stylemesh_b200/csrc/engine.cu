@@ -4,6 +4,7 @@
 // the one-time weight repacking.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -27,6 +28,15 @@ const char* get_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// programmatic dependent launch (smb_common.cuh) is on unless SMB_PDL=0
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 // ---- VGG-19 topology up to conv5_1 (model/losses/content_and_style_losses.py:11-32,47-66) ---------------------
 static const int kCin[SMB_NUM_VGG_CONVS] = {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512};
@@ -204,8 +214,21 @@ static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, c
   if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
   return launch_igemm_simt(a, b, ep, st);
 }
-static int gram(int impl, const Act& fm, float* partial, int nsplit, cudaStream_t st) {
-  return impl == IMPL_TC ? launch_gram_tc(fm, partial, nsplit, st) : launch_gram_simt(fm, partial, nsplit, st);
+// masked Gram partials: the tcgen05 kernel masks pixels in shared memory, the SIMT kernel reads a masked copy
+static int gram(int impl, const Act& f, const float* rowmask, const Act& scratch, float* partial, int nsplit,
+                cudaStream_t st) {
+  if (impl == IMPL_TC) return launch_gram_tc(f, rowmask, partial, nsplit, st);
+  Act src = f;
+  if (rowmask) {
+    Act fm = scratch;
+    fm.H = f.H;
+    fm.W = f.W;
+    fm.C = f.C;
+    int rc = launch_mask_rows(f, rowmask, fm, st);
+    if (rc) return rc;
+    src = fm;
+  }
+  return launch_gram_simt(src, partial, nsplit, st);
 }
 static int igemm_timed(smb_ctx* ctx, int cls, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
   ScopedTimer tm(ctx->timing, cls, st, 2.0 * (double)a.pixels() * b.N * b.K * b.taps);
@@ -220,9 +243,8 @@ static Slot* get_slot(smb_ctx* ctx, int slot) {
   return ctx->slots[slot].get();
 }
 
-static int ensure_scratch(Slot& s, int conv_impl_unused) {
-  (void)conv_impl_unused;
-  if (!s.fm.hi) {
+static int ensure_scratch(Slot& s, int gram_impl) {
+  if (!s.fm.hi && gram_impl != IMPL_TC) {      // masked feature copy: only the SIMT Gram kernel needs one
     int64_t max_elems = 0;
     for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) max_elems = std::max(max_elems, s.y[i].elems());
     s.fm.H = 1;
@@ -248,39 +270,26 @@ static int ensure_gram_partial(Slot& s, int64_t elems) {
   return s.arena.alloc(&s.gram_partial, elems);   // the previous (smaller) block stays in the arena until destroy
 }
 
-// masked Gram partials of layer `conv`; returns the operand actually used (masked copy or the features)
-static int gram_partials(smb_ctx* ctx, Slot& s, int conv, const float* rowmask, Act* used, int* nsplit,
-                         cudaStream_t st) {
-  int rc = ensure_scratch(s, ctx->conv_impl);
+// masked Gram partials of layer `conv`
+static int gram_partials(smb_ctx* ctx, Slot& s, int conv, const float* rowmask, int* nsplit, cudaStream_t st) {
+  int rc = ensure_scratch(s, ctx->gram_impl);
   if (rc) return rc;
-  Act src = s.y[conv];
-  if (rowmask) {
-    Act fm = s.fm;
-    fm.H = src.H;
-    fm.W = src.W;
-    fm.C = src.C;
-    {
-      ScopedTimer tm(ctx->timing, CLS_MISC, st);
-      rc = launch_mask_rows(src, rowmask, fm, st);
-    }
-    if (rc) return rc;
-    src = fm;
-  }
+  const Act& src = s.y[conv];
   const int ns = gram_num_splits(src.pixels(), src.C, ctx->gram_impl);
   rc = ensure_gram_partial(s, (int64_t)ns * src.C * src.C);
   if (rc) return rc;
   {
     ScopedTimer tm(ctx->timing, CLS_GRAM, st, 2.0 * (double)src.pixels() * src.C * src.C);
-    rc = gram(ctx->gram_impl, src, s.gram_partial, ns, st);
+    rc = gram(ctx->gram_impl, src, rowmask, s.fm, s.gram_partial, ns, st);
   }
   if (rc) return rc;
-  *used = src;
   *nsplit = ns;
   return SMB_OK;
 }
 
 __global__ void gram_reduce_kernel(const float* __restrict__ partial, int nsplit, int64_t CC, float inv_n,
                                    float* __restrict__ out) {
+  pdl_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < CC; e += stride) {
     float g = 0.f;
@@ -520,6 +529,7 @@ int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, voi
 
 namespace smb {
 __global__ void act_to_f32_kernel(Act src, float* __restrict__ dst) {
+  pdl_sync();
   const int64_t n2 = src.elems() >> 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
@@ -537,9 +547,7 @@ int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc
               conv, sp->last_done);
   const Act& a = sp->y[conv];
   if (a.elems() == 0) return SMB_OK;
-  smb::act_to_f32_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1, 256), 148 * 16), 256, 0,
-                           (cudaStream_t)stream>>>(a, out_nhwc);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(smb::act_to_f32_kernel, (unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1, 256), 148 * 16), 256, 0, (cudaStream_t)stream, a, out_nhwc);
   return SMB_OK;
 }
 
@@ -557,14 +565,11 @@ int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float
   SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && gram_out, "level_gram: conv %d not computed (last=%d)", conv,
               sp->last_done);
   cudaStream_t st = (cudaStream_t)stream;
-  Act used;
   int ns = 0;
-  int rc = gram_partials(ctx, *sp, conv, rowmask, &used, &ns, st);
+  int rc = gram_partials(ctx, *sp, conv, rowmask, &ns, st);
   if (rc) return rc;
-  const int64_t CC = (int64_t)used.C * used.C;
-  gram_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st>>>(sp->gram_partial, ns, CC,
-                                                                                           inv_n, gram_out);
-  SMB_LAUNCH_CHECK();
+  const int64_t CC = (int64_t)sp->y[conv].C * sp->y[conv].C;
+  SMB_LAUNCH(gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st, sp->gram_partial, ns, CC, inv_n, gram_out);
   return SMB_OK;
 }
 
@@ -582,30 +587,31 @@ int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask,
   SMB_REQUIRE(conv >= 0 && conv <= s.last_done, "style_term: conv %d not computed (last=%d)", conv, s.last_done);
   SMB_REQUIRE(target0 && loss_accum, "style_term: null target or loss accumulator");
   cudaStream_t st = (cudaStream_t)stream;
-  Act used;
+  const Act& feat = s.y[conv];
   int ns = 0;
-  int rc = gram_partials(ctx, s, conv, rowmask, &used, &ns, st);
+  int rc = gram_partials(ctx, s, conv, rowmask, &ns, st);
   if (rc) return rc;
   {
     ScopedTimer tm(ctx->timing, CLS_GRAM_MSE, st);
-    rc = launch_gram_mse(s.gram_partial, ns, used.C, inv_n, target0, coef0, target1, coef1, prev_sum,
+    rc = launch_gram_mse(s.gram_partial, ns, feat.C, inv_n, target0, coef0, target1, coef1, prev_sum,
                          prev_sum ? avg_len : 1.f, gram_out, s.bmat_hi, s.bmat_lo, loss_accum, st);
   }
   if (rc) return rc;
   if (inv_n == 0.f) return SMB_OK;   // empty mask: constant loss, zero gradient (cs:140-141)
   rc = ensure_pend(s, conv);
   if (rc) return rc;
-  // dF[p][c] (+)= sum_k Fm[p][k] * Bmat[c][k]
+  // dF[p][c] (+)= m_p * sum_k F[p][k] * Bmat[c][k]   (m in {0,1}: the row scale equals multiplying the masked features)
   PackedB b;
   b.hi = s.bmat_hi;
   b.lo = s.bmat_lo;
   b.taps = 1;
-  b.N = used.C;
-  b.K = used.C;
+  b.N = feat.C;
+  b.K = feat.C;
   Epilogue ep;
+  ep.rowscale = rowmask;
   ep.out_f32 = s.pend[conv];
   if (s.has_pend[conv]) ep.addend = s.pend[conv];
-  rc = igemm_timed(ctx, CLS_IGEMM_GRAMBWD, used, b, ep, st);
+  rc = igemm_timed(ctx, CLS_IGEMM_GRAMBWD, feat, b, ep, st);
   if (rc) return rc;
   s.has_pend[conv] = true;
   return SMB_OK;
@@ -805,6 +811,7 @@ int smb_unit_maxpool(const float* x, int C, int H, int W, float* y, void* stream
 
 namespace smb {
 __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t P) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * C) return;
   const int64_t p = i / C;
@@ -829,8 +836,7 @@ int smb_unit_maxpool_bwd(const float* g, const float* y, int C, int H, int W, fl
   rc = launch_act_from_nchw(y, ya, st);
   if (rc) return rc;
   if (Pp > 0) {
-    smb::nchw_to_nhwc_f32_kernel<<<(unsigned)ceil_div64(Pp * C, 256), 256, 0, st>>>(g, g_nhwc, C, Pp);
-    SMB_LAUNCH_CHECK();
+    SMB_LAUNCH(smb::nchw_to_nhwc_f32_kernel, (unsigned)ceil_div64(Pp * C, 256), 256, 0, st, g, g_nhwc, C, Pp);
   }
   rc = launch_maxpool_bwd_relu(g_nhwc, nullptr, ya, dz, st);
   if (rc) return rc;
@@ -850,24 +856,18 @@ int smb_unit_gram(int impl, const float* f, int C, int H, int W, const float* ro
   if (rc) return rc;
   rc = launch_act_from_nchw(f, a, st);
   if (rc) return rc;
-  Act src = a;
-  if (rowmask) {
+  if (rowmask && impl != IMPL_TC) {
     rc = ar.alloc_act(&m, H, W, C);
     if (rc) return rc;
-    rc = launch_mask_rows(a, rowmask, m, st);
-    if (rc) return rc;
-    src = m;
   }
-  const int ns = gram_num_splits(src.pixels(), C, impl);
+  const int ns = gram_num_splits(a.pixels(), C, impl);
   float* partial = nullptr;
   rc = ar.alloc(&partial, (int64_t)ns * C * C);
   if (rc) return rc;
-  rc = gram(impl, src, partial, ns, st);
+  rc = gram(impl, a, rowmask, m, partial, ns, st);
   if (rc) return rc;
   const int64_t CC = (int64_t)C * C;
-  smb::gram_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st>>>(partial, ns, CC,
-                                                                                                inv_n, G);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(smb::gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st, partial, ns, CC, inv_n, G);
   SMB_CUDA_CHECK(cudaStreamSynchronize(st));
   return SMB_OK;
 }

@@ -56,6 +56,42 @@ long long launch_count();
     SMB_CUDA_CHECK(cudaGetLastError());    \
   } while (0)
 
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A step is ~80 short launches on one stream; with the attribute below the grid of
+// launch i+1 is scheduled as soon as every CTA of launch i has started (SMB_LAUNCH kernels trigger at their top),
+// so its CTAs take SMs as they drain and run their prologue (barrier init, TMEM alloc, descriptor prefetch) under
+// the tail of launch i.  Contract: every kernel launched through SMB_LAUNCH executes pdl_sync() before its first
+// global-memory access and before any early return (griddepcontrol.wait returns once the preceding grid has
+// completed and its writes are visible; it is a no-op for a launch without the attribute).  SMB_PDL=0 disables.
+// ------------------------------------------------------------------------------------------
+bool pdl_enabled();
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define SMB_LAUNCH(kernel, grid, block, smem, st, ...)                                               \
+  do {                                                                                               \
+    ::smb::count_launch();                                                                           \
+    SMB_CUDA_CHECK(::smb::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)); \
+  } while (0)
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

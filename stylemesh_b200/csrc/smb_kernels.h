@@ -100,9 +100,11 @@ int launch_act_to_nchw(const Act& src, float* dst, cudaStream_t st);
 int launch_mask_rows(const Act& src, const float* rowmask, const Act& dst, cudaStream_t st);
 
 // Gram: partial[s][i][j] = sum_{p in split s} Fm[p][i] * Fm[p][j]   (unnormalised), s in [0, nsplit)
+// The tcgen05 kernel takes the features and the {0,1} pixel mask (nullable) and zeroes masked pixels in shared
+// memory; the SIMT kernel wants the masked copy (launch_mask_rows).
 int gram_num_splits(int64_t P, int C, int impl);
 int launch_gram_simt(const Act& fm, float* partial, int nsplit, cudaStream_t st);
-int launch_gram_tc(const Act& fm, float* partial, int nsplit, cudaStream_t st);
+int launch_gram_tc(const Act& f, const float* rowmask, float* partial, int nsplit, cudaStream_t st);
 
 // Gram loss + gradient seed.  G = inv_n * sum_s partial[s];  if prev_sum: Ghat = (G + prev_sum) / avg_len else Ghat = G
 //   loss_out[0] += sum_t coef[t] * mean((Y_t - Ghat)^2)

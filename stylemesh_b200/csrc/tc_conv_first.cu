@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();                              // prologue (weights are constants) overlaps the preceding launch's tail
 
   if (warp < 4) {
     // ===================== im2col producers: thread r builds row r of the A tile =====================
@@ -213,8 +214,7 @@ int launch_conv_first_tc(const float* img, int H, int W, const __nv_bfloat16* w_
     attr_set = true;
   }
   const int grid = std::min(prm.tiles, 2 * 148);     // two CTAs per SM (83 KB smem, 256 TMEM columns each)
-  conv_first_tc_kernel<<<grid, CF_THREADS, CF_SMEM, st>>>(prm);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(conv_first_tc_kernel, grid, CF_THREADS, CF_SMEM, st, prm);
   return SMB_OK;
 }
 

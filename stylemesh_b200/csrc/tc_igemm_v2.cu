@@ -79,7 +79,10 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   using Cfg = I2Cfg<BN>;
   const long long G = gridDim.x, cta = blockIdx.x;
   const long long u0 = cta * prm.total_units / G, u1 = (cta + 1) * prm.total_units / G;
-  if (u0 >= u1) return;                       // more CTAs than work units (uniform exit, nothing allocated yet)
+  if (u0 >= u1) {                             // more CTAs than work units (uniform exit, nothing allocated yet)
+    pdl_sync();
+    return;
+  }
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -123,6 +126,7 @@ igemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();                                // everything above overlaps the tail of the preceding launch
   if (tr && threadIdx.x == 0) tr[TR_CLK_PROLOGUE] = (unsigned long long)clock64();
 
   if (warp == 0) {
@@ -497,8 +501,7 @@ static int launch_igemm_tc2_bn(const Act& a, const PackedB& b, const Epilogue& e
   // write + read); keep at least ~16 K-iterations per CTA unless that would leave fewer CTAs than tiles
   long long want = std::max<long long>(tiles, prm.total_units / 16);
   const int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(num_sms, prm.total_units), want));
-  igemm_tc2_kernel<BN><<<grid, I2_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(igemm_tc2_kernel<BN>, grid, I2_THREADS, smem_bytes, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
   return SMB_OK;
 }
 

@@ -267,6 +267,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   i5_cluster_sync();                         // peer barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();                                // everything above overlaps the tail of the preceding launch
   if (tr && threadIdx.x == 0) tr[T5_CLK_PROLOGUE] = (unsigned long long)clock64();
 
   if (warp == 0) {
@@ -787,9 +788,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     if (num_sms > 148) num_sms = 148;
   }
   const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units / prm.align));
-  igemm_ph_kernel<BN><<<(unsigned)(2 * pairs), I5_THREADS, Cfg::SMEM, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi,
-                                                                           tmO_lo, prm);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(igemm_ph_kernel<BN>, (unsigned)(2 * pairs), I5_THREADS, Cfg::SMEM, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, prm);
   return SMB_OK;
 }
 

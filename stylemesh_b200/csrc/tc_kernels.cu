@@ -82,6 +82,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -165,7 +166,8 @@ constexpr int GR_BOX_BYTES = GR_KP * 64 * 2;     // one {64 ch, 64 pixel} box = 
 struct GramTcParams {
   int C, nsplit;
   int64_t P, pix_per_split;
-  float* partial;   // [nsplit][C][C]
+  float* partial;          // [nsplit][C][C]
+  const float* rowmask;    // [P] of {0, 1} or nullptr: pixels with mask 0 do not contribute (cs:136-143 compaction)
 };
 
 template <int BN>
@@ -187,7 +189,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* masked_bar = tmem_full_bar + 1;              // [STAGES] count 128: masked pixel rows of B are zeroed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(masked_bar + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * TC_BM, j0 = blockIdx.y * BN, split = blockIdx.z;
@@ -204,6 +207,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&masked_bar[s], 128);
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -216,6 +220,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -244,7 +249,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       for (int it = 0; it < num_iters; ++it) {
         const int stage = it % Cfg::STAGES;
         const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase, 12);
+        mbar_wait(prm.rowmask ? &masked_bar[stage] : &full_bar[stage], phase, 12);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
@@ -270,6 +275,35 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float* out = prm.partial + (int64_t)split * C * C;
+    if (prm.rowmask) {
+      // While the main loop runs these four warps apply the pixel mask: m in {0, 1}, so G = sum_p m_p F_p F_p^T is the
+      // plain product with the masked pixels' rows of ONE operand zeroed.  A pixel is one 128-byte row of every
+      // 64-channel box (the swizzle only permutes 16-byte chunks inside the row): thread t owns pixel t % 64 of the
+      // stage in plane t / 64 (hi, lo) of B.  Generic-proxy stores -> fence.proxy.async -> masked_bar -> MMA.
+      const int t = threadIdx.x - 64, pl = t & 63, plane = t >> 6;
+      auto mask_at = [&](int it) -> float {
+        const int64_t pix = pbeg + (int64_t)it * GR_KP + pl;
+        return (it < num_iters && pix < prm.P) ? __ldg(prm.rowmask + pix) : 1.f;   // rows past P are TMA zero fill
+      };
+      float m = mask_at(0);
+      for (int it = 0; it < num_iters; ++it) {
+        const float m_next = mask_at(it + 1);            // in flight while this stage lands
+        const int stage = it % Cfg::STAGES;
+        const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
+        mbar_wait(&full_bar[stage], phase, 14);
+        if (m == 0.f) {
+          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + plane * Cfg::B_BYTES + pl * 128;
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(rowp + g * GR_BOX_BYTES + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&masked_bar[stage]);
+        m = m_next;
+      }
+    }
     if (num_iters > 0) {
       mbar_wait(tmem_full_bar, 0, 13);
       tc_fence_after();
@@ -360,8 +394,7 @@ static int launch_igemm_tc_bn(const Act& a, const PackedB& b, const Epilogue& ep
     attr_set = true;
   }
   dim3 grid(prm.tiles_x * tiles_y, b.N / BN);
-  igemm_tc_kernel<BN><<<grid, TC_THREADS, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(igemm_tc_kernel<BN>, grid, TC_THREADS, smem_bytes, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
   return SMB_OK;
 }
 
@@ -381,14 +414,15 @@ int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStre
 }
 
 template <int BN>
-static int launch_gram_tc_bn(const Act& fm, float* partial, int nsplit, cudaStream_t st) {
+static int launch_gram_tc_bn(const Act& fm, const float* rowmask, float* partial, int nsplit, cudaStream_t st) {
   using Cfg = GramCfg<BN>;
   GramTcParams prm;
   prm.C = fm.C;
   prm.nsplit = nsplit;
   prm.P = fm.pixels();
-  prm.pix_per_split = ceil_div64(ceil_div64(std::max<int64_t>(prm.P, 1), nsplit), GR_KP) * GR_KP;
+  prm.pix_per_split = ceil_div64(ceil_div64(std::max<int64_t>(prm.P, 1), GR_KP), nsplit) * GR_KP;   // whole 64-pixel stages
   prm.partial = partial;
+  prm.rowmask = rowmask;
   CUtensorMap tm_hi, tm_lo;
   const uint64_t dims[2] = {(uint64_t)fm.C, (uint64_t)std::max<int64_t>(prm.P, 1)};
   const uint64_t strides[1] = {(uint64_t)fm.C * 2};
@@ -404,17 +438,22 @@ static int launch_gram_tc_bn(const Act& fm, float* partial, int nsplit, cudaStre
     attr_set = true;
   }
   dim3 grid(ceil_div(fm.C, TC_BM), fm.C / BN, nsplit);
-  gram_tc_kernel<BN><<<grid, TC_THREADS, smem_bytes, st>>>(tm_hi, tm_lo, prm);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(gram_tc_kernel<BN>, grid, TC_THREADS, smem_bytes, st, tm_hi, tm_lo, prm);
   return SMB_OK;
 }
 
-int launch_gram_tc(const Act& fm, float* partial, int nsplit, cudaStream_t st) {
+// N tile of the Gram kernel.  Every CTA writes a 128 x BN fp32 partial tile and gram_mse reads all of them back, so
+// the partial traffic is nsplit * C^2 * 4 bytes with nsplit ~ 2 * 148 / tiles: wide tiles on the small deep layers
+// (C = 512, P = 4800) moved 39 MB of partials for a 9.8 MB feature map.  C >= 256 therefore uses BN = 64 (4x the
+// tiles, a quarter of the splits and of the partial bytes; the feature map is L2 resident, the tensor pipe is not
+// the limit at 2.5 GFLOP per layer).
+int gram_tc_bn(int C) { return (C >= 256 || C % 128 != 0) ? 64 : 128; }
+
+int launch_gram_tc(const Act& fm, const float* rowmask, float* partial, int nsplit, cudaStream_t st) {
   SMB_REQUIRE(fm.C % 64 == 0, "gram_tc: C=%d must be a multiple of 64", fm.C);
   SMB_REQUIRE(fm.pixels() > 0, "gram_tc: empty feature map");
-  if (fm.C % 256 == 0) return launch_gram_tc_bn<256>(fm, partial, nsplit, st);
-  if (fm.C % 128 == 0) return launch_gram_tc_bn<128>(fm, partial, nsplit, st);
-  return launch_gram_tc_bn<64>(fm, partial, nsplit, st);
+  if (gram_tc_bn(fm.C) == 128) return launch_gram_tc_bn<128>(fm, rowmask, partial, nsplit, st);
+  return launch_gram_tc_bn<64>(fm, rowmask, partial, nsplit, st);
 }
 
 }  // namespace smb

@@ -49,6 +49,7 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fm
 __global__ void __launch_bounds__(256) uv_sample_fwd_kernel(TexLayerSet tex, const float2* __restrict__ grid,
                                                             int npix, float clamp_lo, float clamp_hi,
                                                             float* __restrict__ out) {
+  pdl_sync();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const float2 g = __ldg(grid + p);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) uv_sample_fwd_kernel(TexLayerSet tex, con
 // debug/export: the exact integer texel and the four fp32 weights (for the bit-exact index test)
 __global__ void uv_texel_index_kernel(const float2* __restrict__ grid, int npix, int W, int H,
                                       int* __restrict__ xy0, float* __restrict__ w4) {
+  pdl_sync();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const float2 g = grid[p];
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(256) uv_scatter_bwd_kernel(TexLayerSet gtex, c
                                                              int npix, const float* __restrict__ gout,
                                                              const float* __restrict__ hook0,
                                                              const float* __restrict__ hook1) {
+  pdl_sync();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = p < npix;
   float g[SMB_MAX_TEX_CHANNELS];
@@ -181,6 +184,7 @@ __device__ __forceinline__ void adam_elem(float& p, float& g, float& m, float& v
 __global__ void __launch_bounds__(256) adam_clamp_reg_kernel(float* __restrict__ p, float* __restrict__ g,
                                                              float* __restrict__ m, float* __restrict__ v,
                                                              int64_t n, AdamScalars s) {
+  pdl_sync();
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(256) adam_clamp_reg_kernel(float* __restrict__
 __global__ void __launch_bounds__(256) sumsq_clamped_kernel(const float* __restrict__ x, int64_t n, float coef,
                                                             float clamp_lo, float clamp_hi,
                                                             float* __restrict__ out) {
+  pdl_sync();
   float acc = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -221,17 +226,13 @@ int launch_uv_sample_fwd(const TexLayerSet& tex, const float* grid, int H, int W
                          float* out, cudaStream_t st) {
   const int npix = H * W;
   if (npix == 0) return SMB_OK;
-  uv_sample_fwd_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(tex, reinterpret_cast<const float2*>(grid), npix,
-                                                           clamp_lo, clamp_hi, out);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(uv_sample_fwd_kernel, ceil_div(npix, 256), 256, 0, st, tex, reinterpret_cast<const float2*>(grid), npix, clamp_lo, clamp_hi, out);
   return SMB_OK;
 }
 
 int launch_uv_texel_index(const float* grid, int npix, int W, int H, int* xy0, float* w4, cudaStream_t st) {
   if (npix == 0) return SMB_OK;
-  uv_texel_index_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(reinterpret_cast<const float2*>(grid), npix, W, H,
-                                                            xy0, w4);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(uv_texel_index_kernel, ceil_div(npix, 256), 256, 0, st, reinterpret_cast<const float2*>(grid), npix, W, H, xy0, w4);
   return SMB_OK;
 }
 
@@ -239,9 +240,7 @@ int launch_uv_scatter_bwd(const TexLayerSet& gtex, const float* grid, int H, int
                           const float* hook0, const float* hook1, cudaStream_t st) {
   const int npix = H * W;
   if (npix == 0) return SMB_OK;
-  uv_scatter_bwd_kernel<<<ceil_div(npix, 256), 256, 0, st>>>(gtex, reinterpret_cast<const float2*>(grid), npix,
-                                                            gout, hook0, hook1);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(uv_scatter_bwd_kernel, ceil_div(npix, 256), 256, 0, st, gtex, reinterpret_cast<const float2*>(grid), npix, gout, hook0, hook1);
   return SMB_OK;
 }
 
@@ -265,8 +264,7 @@ int launch_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, flo
   s.gscale = gscale;
   const int64_t n4 = (n + 3) >> 2;
   int blocks = (int)std::min<int64_t>(ceil_div64(n4, 256), (int64_t)148 * 16);
-  adam_clamp_reg_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, s);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(adam_clamp_reg_kernel, blocks, 256, 0, st, p, g, m, v, n, s);
   return SMB_OK;
 }
 
@@ -274,8 +272,7 @@ int launch_sumsq_clamped(const float* x, int64_t n, float coef, float clamp_lo, 
                          cudaStream_t st) {
   if (n == 0) return SMB_OK;
   int blocks = (int)std::min<int64_t>(ceil_div64(n, 256 * 8), (int64_t)148 * 8);
-  sumsq_clamped_kernel<<<blocks, 256, 0, st>>>(x, n, coef, clamp_lo, clamp_hi, out);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(sumsq_clamped_kernel, blocks, 256, 0, st, x, n, coef, clamp_lo, clamp_hi, out);
   return SMB_OK;
 }
 

@@ -16,6 +16,7 @@ namespace smb {
 // layout converters
 // ============================================================================================================
 __global__ void __launch_bounds__(256) act_from_nchw_kernel(const float* __restrict__ src, Act dst) {
+  pdl_sync();
   // one thread per (pixel, 8-channel group); reads are coalesced across pixels for each channel
   const int64_t P = dst.pixels();
   const int groups = dst.C >> 3;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) act_from_nchw_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(256) act_to_nchw_kernel(Act src, float* __restrict__ dst) {
+  pdl_sync();
   const int64_t P = src.pixels();
   const int groups = src.C >> 3;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(Act src, float* __rest
 }
 
 __global__ void __launch_bounds__(256) mask_rows_kernel(Act src, const float* __restrict__ rowmask, Act dst) {
+  pdl_sync();
   const int64_t n8 = src.elems() >> 3;
   const int g_per_row = src.C >> 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(Act src, const float* __
 }
 
 __global__ void __launch_bounds__(256) relu_mask_split_kernel(const float* __restrict__ g, Act y, Act dz) {
+  pdl_sync();
   const int64_t n4 = y.elems() >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(256) relu_mask_split_kernel(const float* __res
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __restrict__ img, int H, int W,
                                                              const float* __restrict__ w_oihw, Epilogue ep) {
+  pdl_sync();
   __shared__ float sw[27][COUT];   // [ci*9 + r*3 + s][co]
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
     const int co = i / 27, k = i % 27;   // w_oihw[co][ci][r][s] is contiguous in k = ci*9+r*3+s
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(128) conv_first_fwd_kernel(const float* __rest
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_first_dgrad_kernel(Act dz, const float* __restrict__ w_oihw,
                                                                float* __restrict__ dimg) {
+  pdl_sync();
   __shared__ float4 sw[9][COUT];    // [r*3+s][co] = (w[co][0][r][s], w[co][1][r][s], w[co][2][r][s], 0)
   for (int i = threadIdx.x; i < 9 * COUT; i += blockDim.x) {
     const int rs = i / COUT, co = i % COUT;
@@ -203,6 +209,7 @@ __device__ __forceinline__ void load8(const Act& a, int64_t off, float (&v)[8], 
 }
 
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(Act in, Act out) {
+  pdl_sync();
   const int groups = in.C >> 3;
   const int64_t total = out.pixels() * groups;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(Act in, Act out) {
 // dz = addend masked by ReLU (or zero).
 __global__ void __launch_bounds__(256, 3) maxpool_bwd_relu_kernel(const float* __restrict__ gp,
                                                                const float* __restrict__ addend, Act y, Act dz) {
+  pdl_sync();
   const int groups = y.C >> 3;
   const int Ho = y.H >> 1, Wo = y.W >> 1;
   const int Hc = (y.H + 1) >> 1, Wc = (y.W + 1) >> 1;
@@ -324,6 +332,7 @@ constexpr int SG_KC = 16;
 constexpr int SG_HALO = SG_TP + 2;
 
 __global__ void __launch_bounds__(128) igemm_simt_kernel(Act a, PackedB b, Epilogue ep, int tiles_x) {
+  pdl_sync();
   __shared__ float As[SG_HALO * SG_HALO][SG_KC + 1];
   __shared__ float Ws[9][SG_BN][SG_KC + 1];
   const int tid = threadIdx.x;
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(128) igemm_simt_kernel(Act a, PackedB b, Epilo
 constexpr int GS_T = 32;   // output tile edge and pixel chunk
 __global__ void __launch_bounds__(256) gram_simt_kernel(Act fm, float* __restrict__ partial, int nsplit,
                                                         int64_t pix_per_split) {
+  pdl_sync();
   __shared__ float Fi[GS_T][GS_T + 1], Fj[GS_T][GS_T + 1];
   const int C = fm.C;
   const int i0 = blockIdx.x * GS_T, j0 = blockIdx.y * GS_T, s = blockIdx.z;
@@ -469,6 +479,7 @@ __global__ void __launch_bounds__(256) gram_mse_kernel(const float* __restrict__
                                                        float* __restrict__ g_out, __nv_bfloat16* __restrict__ b_hi,
                                                        __nv_bfloat16* __restrict__ b_lo,
                                                        float* __restrict__ loss_out) {
+  pdl_sync();
   // block = 32 consecutive Gram elements x 8 split groups: group sg sums partial[sg], partial[sg+8], ... (coalesced
   // 128-byte rows), the groups are combined in a fixed order => deterministic, and no thread walks all splits alone
   __shared__ float s_acc[8][33];
@@ -533,6 +544,7 @@ __global__ void __launch_bounds__(256) content_mse_kernel(Act f, const float* __
                                                           const float* __restrict__ rowmask, float coef_loss,
                                                           float coef_grad, float* __restrict__ addend,
                                                           float* __restrict__ loss_out) {
+  pdl_sync();
   const int64_t n8 = f.elems() >> 3;
   const int g_per_row = f.C >> 3;
   float lacc = 0.f;
@@ -572,28 +584,24 @@ int launch_act_from_nchw(const float* src, const Act& dst, cudaStream_t st) {
   SMB_REQUIRE(dst.C % 8 == 0, "act_from_nchw: C=%d must be a multiple of 8", dst.C);
   const int64_t work = dst.pixels() * (dst.C >> 3);
   if (work == 0) return SMB_OK;
-  act_from_nchw_kernel<<<(unsigned)ceil_div64(work, 256), 256, 0, st>>>(src, dst);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(act_from_nchw_kernel, (unsigned)ceil_div64(work, 256), 256, 0, st, src, dst);
   return SMB_OK;
 }
 int launch_act_to_nchw(const Act& src, float* dst, cudaStream_t st) {
   SMB_REQUIRE(src.C % 8 == 0, "act_to_nchw: C=%d must be a multiple of 8", src.C);
   const int64_t work = src.pixels() * (src.C >> 3);
   if (work == 0) return SMB_OK;
-  act_to_nchw_kernel<<<(unsigned)ceil_div64(work, 256), 256, 0, st>>>(src, dst);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(act_to_nchw_kernel, (unsigned)ceil_div64(work, 256), 256, 0, st, src, dst);
   return SMB_OK;
 }
 int launch_mask_rows(const Act& src, const float* rowmask, const Act& dst, cudaStream_t st) {
   if (src.elems() == 0) return SMB_OK;
-  mask_rows_kernel<<<grid_for(src.elems() >> 3, 256), 256, 0, st>>>(src, rowmask, dst);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(mask_rows_kernel, grid_for(src.elems() >> 3, 256), 256, 0, st, src, rowmask, dst);
   return SMB_OK;
 }
 int launch_relu_mask_split(const float* g, const Act& y, const Act& dz, cudaStream_t st) {
   if (y.elems() == 0) return SMB_OK;
-  relu_mask_split_kernel<<<grid_for(y.elems() >> 2, 256), 256, 0, st>>>(g, y, dz);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(relu_mask_split_kernel, grid_for(y.elems() >> 2, 256), 256, 0, st, g, y, dz);
   return SMB_OK;
 }
 
@@ -604,16 +612,14 @@ int launch_conv_first_fwd(const float* img, int H, int W, const float* w_oihw, c
   ep.bias = bias;
   const int64_t P = (int64_t)H * W;
   if (P == 0) return SMB_OK;
-  conv_first_fwd_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(img, H, W, w_oihw, ep);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(conv_first_fwd_kernel<64>, (unsigned)ceil_div64(P, 128), 128, 0, st, img, H, W, w_oihw, ep);
   return SMB_OK;
 }
 int launch_conv_first_dgrad(const Act& dz, const float* w_oihw, int Cout, float* dimg, cudaStream_t st) {
   SMB_REQUIRE(Cout == 64 && dz.C == 64, "conv_first_dgrad: only Cout=64 is built");
   const int64_t P = dz.pixels();
   if (P == 0) return SMB_OK;
-  conv_first_dgrad_kernel<64><<<(unsigned)ceil_div64(P, 128), 128, 0, st>>>(dz, w_oihw, dimg);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(conv_first_dgrad_kernel<64>, (unsigned)ceil_div64(P, 128), 128, 0, st, dz, w_oihw, dimg);
   return SMB_OK;
 }
 
@@ -621,8 +627,7 @@ int launch_maxpool_fwd(const Act& in, const Act& out, cudaStream_t st) {
   SMB_REQUIRE(out.H == in.H / 2 && out.W == in.W / 2 && out.C == in.C && in.C % 8 == 0, "maxpool_fwd: bad shapes");
   const int64_t work = out.pixels() * (in.C >> 3);
   if (work == 0) return SMB_OK;
-  maxpool_fwd_kernel<<<(unsigned)ceil_div64(work, 256), 256, 0, st>>>(in, out);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(maxpool_fwd_kernel, (unsigned)ceil_div64(work, 256), 256, 0, st, in, out);
   return SMB_OK;
 }
 int launch_maxpool_bwd_relu(const float* g_pooled, const float* addend, const Act& y, const Act& dz,
@@ -630,8 +635,7 @@ int launch_maxpool_bwd_relu(const float* g_pooled, const float* addend, const Ac
   SMB_REQUIRE(y.C % 8 == 0 && dz.C == y.C && dz.H == y.H && dz.W == y.W, "maxpool_bwd: bad shapes");
   const int64_t work = (int64_t)((y.H + 1) / 2) * ((y.W + 1) / 2) * (y.C >> 3);
   if (work == 0) return SMB_OK;
-  maxpool_bwd_relu_kernel<<<(unsigned)ceil_div64(work, 256), 256, 0, st>>>(g_pooled, addend, y, dz);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(maxpool_bwd_relu_kernel, (unsigned)ceil_div64(work, 256), 256, 0, st, g_pooled, addend, y, dz);
   return SMB_OK;
 }
 
@@ -642,27 +646,28 @@ int launch_igemm_simt(const Act& a, const PackedB& b, const Epilogue& ep, cudaSt
   if (a.pixels() == 0) return SMB_OK;
   const int tiles_x = ceil_div(a.W, SG_TP), tiles_y = ceil_div(a.H, SG_TP);
   dim3 grid(tiles_x * tiles_y, b.N / SG_BN);
-  igemm_simt_kernel<<<grid, 128, 0, st>>>(a, b, ep, tiles_x);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(igemm_simt_kernel, grid, 128, 0, st, a, b, ep, tiles_x);
   return SMB_OK;
 }
 
+int gram_tc_bn(int C);   // tc_kernels.cu
+
 int gram_num_splits(int64_t P, int C, int impl) {
   if (P <= 0) return 1;
-  // enough CTAs to cover the chip a couple of times, but at least 64 pixels per split
-  const int tiles = (impl == IMPL_TC) ? std::max(1, (C / 128)) * std::max(1, C / 256) : (C / GS_T) * (C / GS_T);
-  int want = std::max(1, (148 * 2) / std::max(1, tiles));
-  const int64_t max_by_pixels = std::max<int64_t>(1, P / 64);
-  return (int)std::min<int64_t>(want, max_by_pixels);
+  // enough CTAs to cover the chip twice; a split is a whole number of 64-pixel stages and none is empty
+  const int tiles = (impl == IMPL_TC) ? ((C + 127) / 128) * (C / gram_tc_bn(C)) : (C / GS_T) * (C / GS_T);
+  const int64_t want = std::max(1, (148 * 2) / std::max(1, tiles));
+  const int64_t stages = ceil_div64(P, 64);
+  const int64_t per = ceil_div64(stages, std::min(want, stages));
+  return (int)ceil_div64(stages, per);
 }
 
 int launch_gram_simt(const Act& fm, float* partial, int nsplit, cudaStream_t st) {
   SMB_REQUIRE(fm.C % GS_T == 0, "gram_simt: C=%d must be a multiple of 32", fm.C);
   const int64_t P = fm.pixels();
-  const int64_t pps = ceil_div64(ceil_div64(std::max<int64_t>(P, 1), nsplit), 64) * 64;
+  const int64_t pps = ceil_div64(ceil_div64(std::max<int64_t>(P, 1), 64), nsplit) * 64;
   dim3 grid(fm.C / GS_T, fm.C / GS_T, nsplit);
-  gram_simt_kernel<<<grid, 256, 0, st>>>(fm, partial, nsplit, pps);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(gram_simt_kernel, grid, 256, 0, st, fm, partial, nsplit, pps);
   return SMB_OK;
 }
 
@@ -671,18 +676,14 @@ int launch_gram_mse(const float* partial, int nsplit, int C, float inv_n, const 
                     __nv_bfloat16* b_hi, __nv_bfloat16* b_lo, float* loss_out, cudaStream_t st) {
   SMB_REQUIRE(y0 != nullptr && avg_len >= 1.f, "gram_mse: need a target and avg_len >= 1");
   const int64_t CC = (int64_t)C * C;
-  gram_mse_kernel<<<(unsigned)ceil_div64(CC, 32), 256, 0, st>>>(partial, nsplit, C, inv_n, y0, coef0, y1, coef1,
-                                                                 prev_sum, avg_len, g_out, b_hi, b_lo, loss_out);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(gram_mse_kernel, (unsigned)ceil_div64(CC, 32), 256, 0, st, partial, nsplit, C, inv_n, y0, coef0, y1, coef1, prev_sum, avg_len, g_out, b_hi, b_lo, loss_out);
   return SMB_OK;
 }
 
 int launch_content_mse(const Act& f, const float* target_nhwc, const float* rowmask, float coef_loss,
                        float coef_grad, float* addend, float* loss_out, cudaStream_t st) {
   if (f.elems() == 0) return SMB_OK;
-  content_mse_kernel<<<grid_for(f.elems() >> 3, 256, 148 * 8), 256, 0, st>>>(f, target_nhwc, rowmask, coef_loss,
-                                                                            coef_grad, addend, loss_out);
-  SMB_LAUNCH_CHECK();
+  SMB_LAUNCH(content_mse_kernel, grid_for(f.elems() >> 3, 256, 148 * 8), 256, 0, st, f, target_nhwc, rowmask, coef_loss, coef_grad, addend, loss_out);
   return SMB_OK;
 }
 

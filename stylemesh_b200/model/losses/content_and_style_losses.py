@@ -124,7 +124,7 @@ def build_loss_plan(level_sizes, pyramid_masks, angle_degrees, angle_threshold, 
     stats = []
     for (H, W), mask in zip(level_sizes, pyramid_masks):
         entry = {"size": (H, W), "layers": {}}
-        m4 = mask.reshape(1, 1, H, W).float()
+        m4 = (mask.reshape(1, 1, H, W) > 0).float()       # {0,1}: the engine's row masks select pixels (cs:137 `mask > 0`)
         if need_angle_split:
             passed = F.interpolate(angle_degrees, (H, W), mode="bilinear") < angle_threshold      # cs:161
             m_pass4, m_fail4 = m4 * passed, m4 * (~passed)

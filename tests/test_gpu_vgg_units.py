@@ -71,7 +71,8 @@ def test_maxpool_forward_backward(h, w):
 @pytest.mark.parametrize("impl", GRAM_IMPLS)
 @pytest.mark.parametrize("c,h,w,masked", [(64, 24, 32, False), (64, 48, 64, True), (128, 24, 32, True),
                                           (256, 12, 16, False), (512, 6, 8, True), (512, 3, 4, False),
-                                          (256, 31, 37, True)])
+                                          (256, 31, 37, True), (64, 120, 160, True), (512, 60, 80, True),
+                                          (128, 97, 131, True)])
 def test_masked_gram(impl, c, h, w, masked):
     eng = _eng()
     g = torch.Generator().manual_seed(c + h + w)
