@@ -472,36 +472,71 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(Act fm, float* __restric
 // ============================================================================================================
 // Gram-MSE: reduce split partials, normalise, (optional running average), loss, gradient seed matrix
 // ============================================================================================================
-__global__ void __launch_bounds__(256) gram_mse_kernel(const float* __restrict__ partial, int nsplit, int C,
-                                                       float inv_n, const float* __restrict__ y0, float coef0,
-                                                       const float* __restrict__ y1, float coef1,
-                                                       const float* __restrict__ prev_sum, float avg_len,
-                                                       float* __restrict__ g_out, __nv_bfloat16* __restrict__ b_hi,
-                                                       __nv_bfloat16* __restrict__ b_lo,
-                                                       float* __restrict__ loss_out) {
+struct GramMseArgs {
+  const float* partial;
+  int nsplit, C;
+  float inv_n;
+  const float* y0;
+  float coef0;
+  const float* y1;
+  float coef1;
+  const float* prev_sum;
+  float avg_len;
+  float* g_out;
+  __nv_bfloat16 *b_hi, *b_lo;
+  float* loss_out;
+};
+
+// element e of the Gram matrix once its split partials are summed: outputs + this element's share of the loss
+__device__ __forceinline__ float gram_mse_finish(const GramMseArgs& a, int64_t e, float sum, float inv_cc) {
+  const float inv_len = 1.f / a.avg_len;
+  const float g = sum * a.inv_n;
+  if (a.g_out) a.g_out[e] = g;
+  float ghat = g;
+  if (a.prev_sum) ghat = (g + __ldg(a.prev_sum + e)) * inv_len;
+  float d = 0.f, lacc = 0.f;
+  {
+    const float diff = ghat - __ldg(a.y0 + e);
+    lacc = fmaf(a.coef0 * diff, diff, lacc);
+    d = fmaf(a.coef0, diff, d);
+  }
+  if (a.y1) {
+    const float diff = ghat - __ldg(a.y1 + e);
+    lacc = fmaf(a.coef1 * diff, diff, lacc);
+    d = fmaf(a.coef1, diff, d);
+  }
+  // dL/dGhat = 2 d / C^2 ; gradient seed for dF = Fm * Bmat:  Bmat = (2 inv_n / len) * dL/dGhat
+  const float bm = (2.f * a.inv_n * inv_len) * (2.f * d * inv_cc);
+  __nv_bfloat16 h, l;
+  split2(bm, h, l);
+  a.b_hi[e] = h;
+  a.b_lo[e] = l;
+  return lacc;
+}
+
+// Many splits, few elements (C <= 128: up to 148 splits of 4096 / 16384 elements).
+__global__ void __launch_bounds__(256) gram_mse_kernel(const GramMseArgs a) {
   pdl_sync();
   // block = 32 consecutive Gram elements x 8 split groups: group sg sums partial[sg], partial[sg+8], ... (coalesced
   // 128-byte rows), the groups are combined in a fixed order => deterministic, and no thread walks all splits alone
   __shared__ float s_acc[8][33];
-  const int64_t CC = (int64_t)C * C;
+  const int64_t CC = (int64_t)a.C * a.C;
   const float inv_cc = 1.f / (float)CC;
-  const float inv_len = 1.f / avg_len;
   const int lane = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int64_t e = (int64_t)blockIdx.x * 32 + lane;
   float acc = 0.f;
   if (e < CC) {
-    // eight loads in flight per thread, added in the original order (bit-identical sums; a plain loop waits one L2
-    // round trip per split: 15 us per launch at 296 splits)
-    const float* src = partial + e;
+    // eight loads in flight per thread, added in the original order (a plain loop waits one L2 round trip per split)
+    const float* src = a.partial + e;
     int s = sg;
-    for (; s + 56 < nsplit; s += 64) {
-      float a[8];
+    for (; s + 56 < a.nsplit; s += 64) {
+      float v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = __ldg(src + (int64_t)(s + 8 * k) * CC);
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (int64_t)(s + 8 * k) * CC);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc += a[k];
+      for (int k = 0; k < 8; ++k) acc += v[k];
     }
-    for (; s < nsplit; s += 8) acc += __ldg(src + (int64_t)s * CC);
+    for (; s < a.nsplit; s += 8) acc += __ldg(src + (int64_t)s * CC);
   }
   s_acc[sg][lane] = acc;
   __syncthreads();
@@ -511,30 +546,36 @@ __global__ void __launch_bounds__(256) gram_mse_kernel(const float* __restrict__
     float g = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) g += s_acc[k][lane];
-    g *= inv_n;
-    if (g_out) g_out[e] = g;
-    float ghat = g;
-    if (prev_sum) ghat = (g + __ldg(prev_sum + e)) * inv_len;
-    float d = 0.f;
-    {
-      const float diff = ghat - __ldg(y0 + e);
-      lacc = fmaf(coef0 * diff, diff, lacc);
-      d = fmaf(coef0, diff, d);
-    }
-    if (y1) {
-      const float diff = ghat - __ldg(y1 + e);
-      lacc = fmaf(coef1 * diff, diff, lacc);
-      d = fmaf(coef1, diff, d);
-    }
-    // dL/dGhat = 2 d / C^2 ; gradient seed for dF = Fm * Bmat:  Bmat = (2 inv_n / len) * dL/dGhat
-    const float bm = (2.f * inv_n * inv_len) * (2.f * d * inv_cc);
-    __nv_bfloat16 h, l;
-    split2(bm, h, l);
-    b_hi[e] = h;
-    b_lo[e] = l;
+    lacc = gram_mse_finish(a, e, g, inv_cc);
   }
   lacc = warp_sum(lacc);
-  if (lane == 0) atomicAdd(loss_out, lacc * inv_cc);
+  if (lane == 0) atomicAdd(a.loss_out, lacc * inv_cc);
+}
+
+// Few splits, many elements (C >= 256: at most 18 splits of 65536 / 262144 elements): one thread per element walks
+// the splits in order, grid-stride over the matrix, ONE loss atomic per block (the grouped kernel above would issue
+// 8192 same-address atomics at C = 512, which serialise in L2).
+__global__ void __launch_bounds__(256) gram_mse_wide_kernel(const GramMseArgs a) {
+  pdl_sync();
+  const int64_t CC = (int64_t)a.C * a.C;
+  const float inv_cc = 1.f / (float)CC;
+  float lacc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < CC; e += (int64_t)gridDim.x * 256) {
+    const float* src = a.partial + e;
+    float acc = 0.f;
+    int s = 0;
+    for (; s + 8 <= a.nsplit; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (int64_t)(s + k) * CC);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += v[k];
+    }
+    for (; s < a.nsplit; ++s) acc += __ldg(src + (int64_t)s * CC);
+    lacc += gram_mse_finish(a, e, acc, inv_cc);
+  }
+  lacc = block_sum(lacc);
+  if (threadIdx.x == 0) atomicAdd(a.loss_out, lacc * inv_cc);
 }
 
 // ============================================================================================================
@@ -654,9 +695,10 @@ int gram_tc_bn(int C);   // tc_kernels.cu
 
 int gram_num_splits(int64_t P, int C, int impl) {
   if (P <= 0) return 1;
-  // enough CTAs to cover the chip twice; a split is a whole number of 64-pixel stages and none is empty
+  // tcgen05 kernel: one CTA per SM (192 KB ring), so ONE wave of <= 148 CTAs - a second wave pays prologue and
+  // pipeline fill again; a split is a whole number of 64-pixel stages and none is empty
   const int tiles = (impl == IMPL_TC) ? ((C + 127) / 128) * (C / gram_tc_bn(C)) : (C / GS_T) * (C / GS_T);
-  const int64_t want = std::max(1, (148 * 2) / std::max(1, tiles));
+  const int64_t want = std::max(1, (impl == IMPL_TC ? 148 : 148 * 2) / std::max(1, tiles));
   const int64_t stages = ceil_div64(P, 64);
   const int64_t per = ceil_div64(stages, std::min(want, stages));
   return (int)ceil_div64(stages, per);
@@ -676,7 +718,12 @@ int launch_gram_mse(const float* partial, int nsplit, int C, float inv_n, const 
                     __nv_bfloat16* b_hi, __nv_bfloat16* b_lo, float* loss_out, cudaStream_t st) {
   SMB_REQUIRE(y0 != nullptr && avg_len >= 1.f, "gram_mse: need a target and avg_len >= 1");
   const int64_t CC = (int64_t)C * C;
-  SMB_LAUNCH(gram_mse_kernel, (unsigned)ceil_div64(CC, 32), 256, 0, st, partial, nsplit, C, inv_n, y0, coef0, y1, coef1, prev_sum, avg_len, g_out, b_hi, b_lo, loss_out);
+  GramMseArgs a{partial, nsplit, C, inv_n, y0, coef0, y1, coef1, prev_sum, avg_len, g_out, b_hi, b_lo, loss_out};
+  if (nsplit <= 32 && CC >= 65536) {
+    SMB_LAUNCH(gram_mse_wide_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 148 * 4), 256, 0, st, a);
+  } else {
+    SMB_LAUNCH(gram_mse_kernel, (unsigned)ceil_div64(CC, 32), 256, 0, st, a);
+  }
   return SMB_OK;
 }
 
