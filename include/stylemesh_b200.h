@@ -158,6 +158,11 @@ int smb_debug_set_igemm_trace(void* buf);
  * transpose_flip != 0 computes the data gradient instead: x is dY (Cout,H,W), y is dX (Cin,H,W), no bias. */
 int smb_unit_conv3x3(int impl, const float* x, int Cin, int H, int W, const float* w_host, const float* b_host,
                      int Cout, int relu, int transpose_flip, float* y, void* stream);
+/* y (Cout,H,W) = conv3x3(x (Cin,H,W), w (Cout,Cin,3,3)) + m * (g f): the pair + halo kernel with a fused 1x1 term
+ * (f (Cout,H,W) device, g (Cout,Cout) host, rowmask (H*W) device {0,1} or NULL) - the Gram backward folded into a
+ * data-gradient conv (model/losses/content_and_style_losses.py:74-80 backward). */
+int smb_unit_conv3x3_fused(const float* x, int Cin, int H, int W, const float* w_host, int Cout, const float* f,
+                           const float* g_host, const float* rowmask, float* y, void* stream);
 /* y (C,H/2,W/2) = maxpool2x2(x (C,H,W)) */
 int smb_unit_maxpool(const float* x, int C, int H, int W, float* y, void* stream);
 /* dx (C,H,W) = maxpool/relu backward of g (C,H/2,W/2) through y (C,H,W) */

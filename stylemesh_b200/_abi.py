@@ -56,6 +56,7 @@ PROTOTYPES = [
     ("smb_ctx_device_bytes", _i64, [_p]),
     ("smb_debug_set_igemm_trace", _i, [_p]),
     ("smb_unit_conv3x3", _i, [_i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
+    ("smb_unit_conv3x3_fused", _i, [_p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
     ("smb_unit_maxpool", _i, [_p, _i, _i, _i, _p, _p]),
     ("smb_unit_maxpool_bwd", _i, [_p, _p, _i, _i, _i, _p, _p]),
     ("smb_unit_gram", _i, [_i, _p, _i, _i, _i, _p, _f, _p, _p]),

@@ -96,6 +96,12 @@ struct Slot {
   float* gram_partial = nullptr;
   int64_t gram_partial_elems = 0;
   __nv_bfloat16 *bmat_hi = nullptr, *bmat_lo = nullptr;
+  // Style term whose Gram backward is deferred into the data-gradient conv of the layer above (igemm_ph fused 1x1
+  // term): its seed matrix and a private copy of its pixel mask live until smb_level_backward.
+  __nv_bfloat16* fb_hi[SMB_NUM_VGG_CONVS];
+  __nv_bfloat16* fb_lo[SMB_NUM_VGG_CONVS];
+  float* fmask[SMB_NUM_VGG_CONVS];
+  bool fused[SMB_NUM_VGG_CONVS], fused_masked[SMB_NUM_VGG_CONVS];
   int last_done = -1;
   DeviceArena arena;
   Slot() {
@@ -103,6 +109,9 @@ struct Slot {
       pend[i] = nullptr;
       has_pend[i] = false;
       gpool[i] = nullptr;
+      fb_hi[i] = fb_lo[i] = nullptr;
+      fmask[i] = nullptr;
+      fused[i] = fused_masked[i] = false;
     }
   }
 };
@@ -205,9 +214,14 @@ static void pack_dgrad(const float* w, int Cout, int Cin, std::vector<float>& ou
           out[((size_t)(r * 3 + s) * Cin + ci) * Cout + co] = w[(((size_t)co * Cin + ci) * 3 + (2 - r)) * 3 + (2 - s)];
 }
 
-static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st,
+                 const FusedTerm* ft = nullptr) {
+  if (ft && !(impl == IMPL_TC_PH && b.taps == 9 && b.N % 64 == 0)) {
+    set_error("fused 1x1 term needs the igemm_ph 3x3 kernel");
+    return SMB_ERR_STATE;
+  }
   if (impl == IMPL_TC_PH)
-    return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
+    return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st, ft) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_HALO) return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_halo(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_PAIR) return (b.N % 128 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
@@ -230,9 +244,20 @@ static int gram(int impl, const Act& f, const float* rowmask, const Act& scratch
   }
   return launch_gram_simt(src, partial, nsplit, st);
 }
-static int igemm_timed(smb_ctx* ctx, int cls, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  ScopedTimer tm(ctx->timing, cls, st, 2.0 * (double)a.pixels() * b.N * b.K * b.taps);
-  return igemm(ctx->conv_impl, a, b, ep, st);
+static int igemm_timed(smb_ctx* ctx, int cls, const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st,
+                       const FusedTerm* ft = nullptr) {
+  const double fl = 2.0 * (double)a.pixels() * b.N * b.K * b.taps + (ft ? 2.0 * (double)a.pixels() * b.N * ft->g.K : 0.0);
+  ScopedTimer tm(ctx->timing, cls, st, fl);
+  return igemm(ctx->conv_impl, a, b, ep, st, ft);
+}
+
+// SMB_PH_FUSE=0 keeps every Gram backward as its own launch (fp32 pending gradient + addend read in the conv epilogue)
+static bool fuse_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMB_PH_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 static Slot* get_slot(smb_ctx* ctx, int slot) {
@@ -268,6 +293,33 @@ static int ensure_gram_partial(Slot& s, int64_t elems) {
   if (s.gram_partial_elems >= elems) return SMB_OK;
   s.gram_partial_elems = elems;
   return s.arena.alloc(&s.gram_partial, elems);   // the previous (smaller) block stays in the arena until destroy
+}
+
+static int ensure_pend(Slot& s, int conv) {
+  if (s.pend[conv]) return SMB_OK;
+  return s.arena.alloc(&s.pend[conv], s.y[conv].elems());
+}
+
+// pend[conv][p][c] (+)= m_p * sum_k F[p][k] * Bmat[c][k]   (m in {0,1}: the row scale equals multiplying masked features)
+static int gram_backward_to_pend(smb_ctx* ctx, Slot& s, int conv, __nv_bfloat16* b_hi, __nv_bfloat16* b_lo,
+                                 const float* rowmask, cudaStream_t st) {
+  int rc = ensure_pend(s, conv);
+  if (rc) return rc;
+  const Act& feat = s.y[conv];
+  PackedB b;
+  b.hi = b_hi;
+  b.lo = b_lo;
+  b.taps = 1;
+  b.N = feat.C;
+  b.K = feat.C;
+  Epilogue ep;
+  ep.rowscale = rowmask;
+  ep.out_f32 = s.pend[conv];
+  if (s.has_pend[conv]) ep.addend = s.pend[conv];
+  rc = igemm_timed(ctx, CLS_IGEMM_GRAMBWD, feat, b, ep, st);
+  if (rc) return rc;
+  s.has_pend[conv] = true;
+  return SMB_OK;
 }
 
 // masked Gram partials of layer `conv`
@@ -505,7 +557,7 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
     if (rc) return rc;
   }
   s.last_done = last_conv;
-  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = s.fused[i] = false;
   return SMB_OK;
 }
 
@@ -573,11 +625,6 @@ int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float
   return SMB_OK;
 }
 
-static int ensure_pend(Slot& s, int conv) {
-  if (s.pend[conv]) return SMB_OK;
-  return s.arena.alloc(&s.pend[conv], s.y[conv].elems());
-}
-
 int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask, float inv_n, const float* target0,
                          float coef0, const float* target1, float coef1, const float* prev_sum, float avg_len,
                          float* gram_out, float* loss_accum, void* stream) {
@@ -591,30 +638,38 @@ int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask,
   int ns = 0;
   int rc = gram_partials(ctx, s, conv, rowmask, &ns, st);
   if (rc) return rc;
+  // Gram backward dF = m * (F . Bmat): folded into the data-gradient conv of the layer above when that conv runs on
+  // igemm_ph at the same resolution (conv1_2, conv2_2, conv3_2, conv4_2 for r11..r41); resolved in smb_level_backward
+  const bool defer = fuse_enabled() && ctx->conv_impl == IMPL_TC_PH && inv_n != 0.f && !s.fused[conv] &&
+                     conv + 1 <= s.last_done && !kPoolBefore[conv + 1];
+  __nv_bfloat16 *b_hi = s.bmat_hi, *b_lo = s.bmat_lo;
+  if (defer) {
+    if (!s.fb_hi[conv]) {
+      rc = s.arena.alloc(&s.fb_hi[conv], (int64_t)feat.C * feat.C);
+      if (rc) return rc;
+      rc = s.arena.alloc(&s.fb_lo[conv], (int64_t)feat.C * feat.C);
+      if (rc) return rc;
+      rc = s.arena.alloc(&s.fmask[conv], feat.pixels());
+      if (rc) return rc;
+    }
+    b_hi = s.fb_hi[conv];
+    b_lo = s.fb_lo[conv];
+  }
   {
     ScopedTimer tm(ctx->timing, CLS_GRAM_MSE, st);
     rc = launch_gram_mse(s.gram_partial, ns, feat.C, inv_n, target0, coef0, target1, coef1, prev_sum,
-                         prev_sum ? avg_len : 1.f, gram_out, s.bmat_hi, s.bmat_lo, loss_accum, st);
+                         prev_sum ? avg_len : 1.f, gram_out, b_hi, b_lo, loss_accum, st);
   }
   if (rc) return rc;
   if (inv_n == 0.f) return SMB_OK;   // empty mask: constant loss, zero gradient (cs:140-141)
-  rc = ensure_pend(s, conv);
-  if (rc) return rc;
-  // dF[p][c] (+)= m_p * sum_k F[p][k] * Bmat[c][k]   (m in {0,1}: the row scale equals multiplying the masked features)
-  PackedB b;
-  b.hi = s.bmat_hi;
-  b.lo = s.bmat_lo;
-  b.taps = 1;
-  b.N = feat.C;
-  b.K = feat.C;
-  Epilogue ep;
-  ep.rowscale = rowmask;
-  ep.out_f32 = s.pend[conv];
-  if (s.has_pend[conv]) ep.addend = s.pend[conv];
-  rc = igemm_timed(ctx, CLS_IGEMM_GRAMBWD, feat, b, ep, st);
-  if (rc) return rc;
-  s.has_pend[conv] = true;
-  return SMB_OK;
+  if (defer) {
+    if (rowmask)      // the caller's mask tensor need not outlive this call
+      SMB_CUDA_CHECK(cudaMemcpyAsync(s.fmask[conv], rowmask, feat.pixels() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    s.fused[conv] = true;
+    s.fused_masked[conv] = rowmask != nullptr;
+    return SMB_OK;
+  }
+  return gram_backward_to_pend(ctx, s, conv, s.bmat_hi, s.bmat_lo, rowmask, st);
 }
 
 int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target_nhwc, const float* rowmask,
@@ -646,9 +701,17 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int top = -1;
   for (int i = s.last_done; i >= 0; --i)
-    if (s.has_pend[i]) {
+    if (s.has_pend[i] || s.fused[i]) {
       top = i;
       break;
+    }
+  // deferred Gram backwards that no data-gradient conv can absorb (the top of the chain, or another conv kernel
+  // selected since) become ordinary pending gradients now
+  for (int i = 0; i <= top; ++i)
+    if (s.fused[i] && (i == top || ctx->conv_impl != IMPL_TC_PH)) {
+      int rc = gram_backward_to_pend(ctx, s, i, s.fb_hi[i], s.fb_lo[i], s.fused_masked[i] ? s.fmask[i] : nullptr, st);
+      if (rc) return rc;
+      s.fused[i] = false;
     }
   if (top < 0) {   // no loss term touched this level: zero gradient
     SMB_CUDA_CHECK(cudaMemsetAsync(d_image, 0, (size_t)3 * s.H * s.W * sizeof(float), st));
@@ -686,7 +749,16 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
       ep.sign_hi = s.y[j].hi;
       ep.out_hi = s.dz[j].hi;
       ep.out_lo = s.dz[j].lo;
-      rc = igemm_timed(ctx, CLS_IGEMM_DGRAD, s.dz[i], ctx->conv[i].dgrad, ep, st);
+      FusedTerm ft;
+      if (s.fused[j]) {
+        ft.f = s.y[j];
+        ft.g.hi = s.fb_hi[j];
+        ft.g.lo = s.fb_lo[j];
+        ft.g.taps = 1;
+        ft.g.N = ft.g.K = s.y[j].C;
+        ft.rowmask = s.fused_masked[j] ? s.fmask[j] : nullptr;
+      }
+      rc = igemm_timed(ctx, CLS_IGEMM_DGRAD, s.dz[i], ctx->conv[i].dgrad, ep, st, s.fused[j] ? &ft : nullptr);
       if (rc) return rc;
     }
   }
@@ -701,7 +773,7 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
     }
   }
   if (rc) return rc;
-  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = false;
+  for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = s.fused[i] = false;
   return SMB_OK;
 }
 
@@ -783,6 +855,44 @@ int smb_unit_conv3x3(int impl, const float* x, int Cin, int H, int W, const floa
   ep.out_hi = o.hi;
   ep.out_lo = o.lo;
   rc = igemm(impl, a, b, ep, st);
+  if (rc) return rc;
+  rc = launch_act_to_nchw(o, y, st);
+  if (rc) return rc;
+  SMB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return SMB_OK;
+}
+
+int smb_unit_conv3x3_fused(const float* x, int Cin, int H, int W, const float* w_host, int Cout, const float* f,
+                           const float* g_host, const float* rowmask, float* y, void* stream) {
+  SMB_REQUIRE(x && w_host && f && g_host && y, "unit_conv3x3_fused: null argument");
+  SMB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "unit_conv3x3_fused: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceArena ar;
+  Act a, o;
+  FusedTerm ft;
+  int rc = ar.alloc_act(&a, H, W, Cin);
+  if (rc) return rc;
+  rc = ar.alloc_act(&o, H, W, Cout);
+  if (rc) return rc;
+  rc = ar.alloc_act(&ft.f, H, W, Cout);
+  if (rc) return rc;
+  std::vector<float> tmp;
+  PackedB b;
+  pack_fwd(w_host, Cout, Cin, tmp);
+  rc = upload_packed(ar, &b, tmp, 9, Cout, Cin);
+  if (rc) return rc;
+  tmp.assign(g_host, g_host + (size_t)Cout * Cout);
+  rc = upload_packed(ar, &ft.g, tmp, 1, Cout, Cout);
+  if (rc) return rc;
+  ft.rowmask = rowmask;
+  rc = launch_act_from_nchw(x, a, st);
+  if (rc) return rc;
+  rc = launch_act_from_nchw(f, ft.f, st);
+  if (rc) return rc;
+  Epilogue ep;
+  ep.out_hi = o.hi;
+  ep.out_lo = o.lo;
+  rc = igemm(IMPL_TC_PH, a, b, ep, st, &ft);
   if (rc) return rc;
   rc = launch_act_to_nchw(o, y, st);
   if (rc) return rc;

@@ -79,7 +79,16 @@ int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStre
 int launch_igemm_tc2(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v2: persistent stream-K
 int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v3: v2 on CTA pairs (N % 128 == 0)
 void set_igemm_trace(unsigned long long* buf);   // tc_igemm_v2.cu: per-CTA timeline of the following launches
-int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);    // v5: CTA pair + A halo + TMA-store epilogue (3x3 only)
+// Optional 1x1 term accumulated by igemm_ph into the same tile before the epilogue:
+//   acc[p][n] += rowmask[p] * sum_k f[p][k] * g[n][k]       (Gram backward of the layer that receives the gradient:
+//   f = its forward features, g = the symmetric seed matrix of gram_mse, rowmask = the term's {0,1} pixel mask)
+struct FusedTerm {
+  Act f;                            // same H x W as the conv input, C a multiple of 64
+  PackedB g;                        // taps == 1, N == conv N, K == f.C
+  const float* rowmask = nullptr;   // [H*W] or nullptr
+};
+int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st,
+                    const FusedTerm* ft = nullptr);    // v5: CTA pair + A halo + TMA-store epilogue (3x3 only)
 int launch_igemm_halo(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);  // v4: 3x3 only, A halo reused by 9 taps
 
 // first layer (3 -> 64) from the fp32 planar image and its data gradient (64 -> 3)

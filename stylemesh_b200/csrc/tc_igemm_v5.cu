@@ -28,6 +28,7 @@ namespace smb {
 using namespace tc;
 
 constexpr int I5_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int I5_THREADS_MASK = 384;                  // + warps 10-11: pixel mask of a fused 1x1 term (launched only then)
 constexpr int I5_EPI_THREADS = 256;
 constexpr int I5_BM = 128;                            // pixel rows per CTA (the pair covers 256)
 constexpr int I5_TH = 16, I5_TW = 8;                  // output patch of one CTA: 16 rows x 8 pixels
@@ -57,6 +58,10 @@ struct I5Cfg {
 
 struct IGemm5Params {
   int H, W, tiles_x, tiles_m, tiles_n, kchunks, N;
+  const float* fmask;         // [H*W] {0,1} pixel mask of the fused term (rows of F with mask 0 do not contribute) or nullptr
+  int kreg;                   // K-chunks kc < kreg are the 3x3 conv (A = input halo, 9 taps of B); chunks kc >= kreg are a
+                              // fused 1x1 term D += F * G^T (Gram backward of the layer receiving the gradient): A = halo of
+                              // F (tmF), only the centre tap multiplies, B = G (tmG).  kreg == kchunks: plain conv.
   long long total_units;      // pair_tiles * kchunks * 9 work units (one tap of one K-chunk of one pair tile)
   int align;                  // stream-K range boundaries are multiples of this many units: 9 (whole halo units) or 1
   float* ws;                  // [grid][128][BN] fp32 partial tiles (indexed by CTA id)
@@ -95,6 +100,13 @@ __device__ __forceinline__ void i5_tma_load_3d(void* dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & I5_PEER_MASK), "r"(c0), "r"(c1),
       "r"(c2)
+      : "memory");
+}
+// same load, completion credited to a barrier of the executing CTA
+__device__ __forceinline__ void i5_tma_load_3d_local(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void i5_tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
@@ -173,6 +185,34 @@ __device__ __forceinline__ void i5_arrive_cta(uint64_t* bar, uint32_t cta) {
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// cluster-scope release / acquire pair for data written by the generic proxy of either CTA (mask warps -> MMA issuer)
+__device__ __forceinline__ void i5_arrive_cta_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void i5_wait_cluster(uint64_t* bar, uint32_t parity, int who) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("[smb] igemm_ph watchdog: wait #%d timed out in block %d thread %d\n", who, (int)blockIdx.x,
+             (int)threadIdx.x);
+      asm volatile("trap;");
+    }
+  }
+}
 __device__ __forceinline__ unsigned int i5_ld_acquire(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -197,10 +237,12 @@ __device__ __forceinline__ void i5_sts128(uint32_t addr, const uint4& v) {
 }
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I5_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I5_THREADS_MASK, 1)
 igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                const __grid_constant__ CUtensorMap tmF_hi, const __grid_constant__ CUtensorMap tmF_lo,
+                const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
                 const IGemm5Params prm) {
   using Cfg = I5Cfg<BN>;
   constexpr int NB = Cfg::NB;
@@ -223,7 +265,9 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* b_empty = b_full + I5_MAX_NB;                     // [NB] both CTAs
   uint64_t* tmem_full_bar = b_empty + I5_MAX_NB;              // [2]  both CTAs
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;               // [2]  used in the leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* f_land = tmem_empty_bar + 2;                      // [2]  both CTAs: own halo of a MASKED fused chunk has landed
+  uint64_t* a_masked = f_land + 2;                            // [2]  used in the leader: both halos landed and masked
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_masked + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ipt = prm.kchunks;                                // (K-chunk) halo loads per pair tile
@@ -246,11 +290,19 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       tma_prefetch_desc(&tmO_hi);
       tma_prefetch_desc(&tmO_lo);
     }
+    if (prm.kreg < prm.kchunks) {
+      tma_prefetch_desc(&tmF_hi);
+      tma_prefetch_desc(&tmF_lo);
+      tma_prefetch_desc(&tmG_hi);
+      tma_prefetch_desc(&tmG_lo);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 16);     // 8 epilogue warps of each CTA
+      mbar_init(&f_land[s], 1);
+      mbar_init(&a_masked[s], 4);            // 2 mask warps of each CTA
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&b_full[s], 1);
@@ -300,10 +352,20 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         } else {
           const int m_tile = 2 * nxt.pm + (int)rank;
           const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
-          if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);      // bytes of both CTAs
+          const bool to_mask = prm.fmask && nxt.kc >= prm.kreg;
+          if (to_mask) mbar_arrive_expect_tx(&f_land[abuf], I5_A_TX);            // own bytes, own barrier
+          else if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);  // bytes of both CTAs
           uint8_t* ah = sA + abuf * I5_A_BUF;
-          i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
-          i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
+          if (nxt.kc < prm.kreg) {
+            i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
+            i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
+          } else if (!prm.fmask) {               // fused 1x1 term: same halo geometry on the feature tensor
+            i5_tma_load_3d(ah, &tmF_hi, &a_full[abuf], (nxt.kc - prm.kreg) * 64, x0 - 1, y0 - 1);
+            i5_tma_load_3d(ah + I5_A_PLANE, &tmF_lo, &a_full[abuf], (nxt.kc - prm.kreg) * 64, x0 - 1, y0 - 1);
+          } else {                               // ... masked: lands on this CTA's own barrier, the mask warps pass it on
+            i5_tma_load_3d_local(ah, &tmF_hi, &f_land[abuf], (nxt.kc - prm.kreg) * 64, x0 - 1, y0 - 1);
+            i5_tma_load_3d_local(ah + I5_A_PLANE, &tmF_lo, &f_land[abuf], (nxt.kc - prm.kreg) * 64, x0 - 1, y0 - 1);
+          }
         }
         nxt.next(ipt, prm.tiles_n);
         ++a_next;
@@ -331,21 +393,29 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (prm.knob & 1) issue_A(tap == 8);
           else if (tap >= 3) issue_A(true);
         }
-        const long long tw0 = tr ? clock64() : 0;
-        mbar_wait(&b_empty[bs], bpar, 62);
-        if (tr) w_empty += clock64() - tw0;
-        if (prm.knob & 8) {
-          if (rank == 0) mbar_arrive(&b_full[bs]);
-        } else {
-          if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_STAGE);
-          uint8_t* bh = sB + bs * Cfg::B_STAGE;
-          const int nb0 = cur.n_tile * BN + (int)rank * (BN / 2);
-          i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], cur.kc * 64, nb0, tap);
-          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], cur.kc * 64, nb0, tap);
-        }
-        if (++bs == NB) {
-          bs = 0;
-          bpar ^= 1u;
+        const bool fused = cur.kc >= prm.kreg;
+        if (!fused || tap == 4) {                // a fused chunk has one B tile (centre tap), the other taps are no-ops
+          const long long tw0 = tr ? clock64() : 0;
+          mbar_wait(&b_empty[bs], bpar, 62);
+          if (tr) w_empty += clock64() - tw0;
+          if (prm.knob & 8) {
+            if (rank == 0) mbar_arrive(&b_full[bs]);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_STAGE);
+            uint8_t* bh = sB + bs * Cfg::B_STAGE;
+            const int nb0 = cur.n_tile * BN + (int)rank * (BN / 2);
+            if (!fused) {
+              i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], cur.kc * 64, nb0, tap);
+              i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], cur.kc * 64, nb0, tap);
+            } else {
+              i5_tma_load_3d(bh, &tmG_hi, &b_full[bs], (cur.kc - prm.kreg) * 64, nb0, 0);
+              i5_tma_load_3d(bh + Cfg::B_PLANE, &tmG_lo, &b_full[bs], (cur.kc - prm.kreg) * 64, nb0, 0);
+            }
+          }
+          if (++bs == NB) {
+            bs = 0;
+            bpar ^= 1u;
+          }
         }
         if (++tap == 9) {
           tap = 0;
@@ -374,6 +444,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       int w = (int)u0;
       int tap = w % 9, ga = 0, bs = 0, seg = 0;
       uint32_t bfpar = 0, a_word = 0;
+      uint32_t par_full = 0, par_masked = 0;   // bit b = parity of the next phase of a_full[b] / a_masked[b]
       int abuf = 0;
       long long w_full = 0, w_tempty = 0;
       bool first = true;
@@ -388,52 +459,66 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc_fence_after();
         const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
         const uint32_t t_corr = t_main + (uint32_t)BN;
+        int kc = ks / 9;                         // K-chunk of unit t (t = kc * 9 + tap)
+        uint32_t started = 0;                    // 0 until the first MMA of this segment has initialised the accumulators
 #pragma unroll 1
         for (int t = ks; t < ke; ++t) {
           if (t == ks || tap == 0) {             // first tap of a halo unit inside this range: its halo must have landed
             abuf = ga & 1;
             const long long tw2 = tr ? clock64() : 0;
-            mbar_wait(&a_full[abuf], (uint32_t)((ga >> 1) & 1), 64);
+            if (prm.fmask && kc >= prm.kreg) {   // masked fused chunk: both CTAs' mask warps have passed the halo on
+              i5_wait_cluster(&a_masked[abuf], (par_masked >> abuf) & 1u, 67);
+              par_masked ^= 1u << abuf;
+            } else {
+              mbar_wait(&a_full[abuf], (par_full >> abuf) & 1u, 64);
+              par_full ^= 1u << abuf;
+            }
             if (tr) w_full += clock64() - tw2;
             a_word = a_word0 + (uint32_t)abuf * (uint32_t)(I5_A_BUF >> 4);
           }
-          if (prm.resident) {                    // stage = tap, loaded once (phase 0 stays complete)
-            bs = tap;
-            bfpar = 0;
-          }
-          const long long tw3 = tr ? clock64() : 0;
-          mbar_wait(&b_full[bs], bfpar, 65);
-          if (tr) {
-            const long long now = clock64();
-            w_full += now - tw3;
-            if (first) tr[T5_CLK_MMA_FIRST] = (unsigned long long)now;
-            first = false;
-          }
-          tc_fence_after();
-          const int dy = (tap >= 6) ? 2 : (tap >= 3 ? 1 : 0);
-          const uint32_t a_t = a_word + (uint32_t)(dy * (I5_PITCH >> 4) + (tap - 3 * dy) * 8);   // halo coords of the tap
-          const uint32_t b_t = b_word0 + (uint32_t)bs * (uint32_t)(Cfg::B_STAGE >> 4);
-          if (!(prm.knob & 4)) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t acc = (uint32_t)((t > ks) || (k > 0));
-              i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
-              i5_umma2(t_corr, a_t + 2 * k, HI_A, b_t + B_LO_PLANE + 2 * k, HI_B, idesc, 1u);
-              i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+          if (kc < prm.kreg || tap == 4) {       // (a fused 1x1 chunk multiplies its centre tap only)
+            if (prm.resident) {                  // stage = tap, loaded once (phase 0 stays complete)
+              bs = tap;
+              bfpar = 0;
             }
-          }
-          if (!prm.resident) {
-            i5_commit_mc(&b_empty[bs]);          // frees this B stage in BOTH CTAs
-            if (++bs == NB) {
-              bs = 0;
-              bfpar ^= 1u;
+            const long long tw3 = tr ? clock64() : 0;
+            mbar_wait(&b_full[bs], bfpar, 65);
+            if (tr) {
+              const long long now = clock64();
+              w_full += now - tw3;
+              if (first) tr[T5_CLK_MMA_FIRST] = (unsigned long long)now;
+              first = false;
+            }
+            tc_fence_after();
+            const int dy = (tap >= 6) ? 2 : (tap >= 3 ? 1 : 0);
+            const uint32_t a_t = a_word + (uint32_t)(dy * (I5_PITCH >> 4) + (tap - 3 * dy) * 8);   // halo coords of the tap
+            const uint32_t b_t = b_word0 + (uint32_t)bs * (uint32_t)(Cfg::B_STAGE >> 4);
+            if (!(prm.knob & 4)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = started | (uint32_t)(k > 0);
+                i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+                i5_umma2(t_corr, a_t + 2 * k, HI_A, b_t + B_LO_PLANE + 2 * k, HI_B, idesc, 1u);
+                i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+              }
+            }
+            started = 1u;
+            if (!prm.resident) {
+              i5_commit_mc(&b_empty[bs]);        // frees this B stage in BOTH CTAs
+              if (++bs == NB) {
+                bs = 0;
+                bfpar ^= 1u;
+              }
             }
           }
           if (tap == 8 || t == ke - 1) {         // last tap of this halo unit inside the range
             i5_commit_mc(&a_empty[abuf]);        // frees this halo buffer in BOTH CTAs
             ++ga;
           }
-          if (++tap == 9) tap = 0;
+          if (++tap == 9) {
+            tap = 0;
+            ++kc;
+          }
         }
         i5_commit_mc(&tmem_full_bar[buf]);       // accumulators complete, both CTAs
         w += (ke - ks);
@@ -445,7 +530,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tr[T5_W_TMEM_EMPTY] = (unsigned long long)w_tempty;
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ===================== epilogue warps (each CTA drains its own 128 TMEM lanes) =====================
     // warps 2-5 and 6-9 both cover the four TMEM lane quarters (quarter = warp % 4); set 0 takes the first 32
     // channels of every 64-channel group, set 1 the second 32, and they meet at the staging buffer / named barrier
@@ -667,6 +752,46 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       tr[T5_W_FLAGS] = (unsigned long long)w_flags;
       tr[T5_W_TMEM_FULL] = (unsigned long long)w_tfull;
     }
+  } else if (prm.fmask && prm.kreg < prm.kchunks) {
+    // ===================== mask warps (10-11; launched only for a masked fused term) =====================
+    // m in {0,1}: m_p * (F_p . G) is the product with the masked pixels' rows of F zeroed.  A pixel is one 128-byte
+    // row of the halo (the swizzle permutes 16-byte chunks inside it); only the centre 16 x 8 pixels are read by the
+    // centre tap.  Each CTA masks its own halo (landed on its own f_land barrier) and hands it to the leader's MMA
+    // thread through a_masked (4 warp arrivals, cluster-scope release after a proxy fence).
+    const int tid = (int)threadIdx.x - I5_THREADS;                 // 0..63
+    const int h0 = (int)(u0 / 9), h1 = (int)((u1 + 8) / 9);        // fused launches split at whole halo units
+    UnitWalk wk;
+    wk.init(h0, ipt, prm.tiles_n);
+    uint32_t par = 0;                                              // bit b = parity of the next phase of f_land[b]
+    for (int h = h0; h < h1; ++h, wk.next(ipt, prm.tiles_n)) {
+      if (wk.kc < prm.kreg) continue;
+      const int abuf = (h - h0) & 1;
+      const int m_tile = 2 * wk.pm + (int)rank;
+      const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
+      float m[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = tid + 64 * j, y = y0 + (r >> 3), x = x0 + (r & 7);
+        m[j] = (y < prm.H && x < prm.W) ? __ldg(prm.fmask + (int64_t)y * prm.W + x) : 1.f;   // outside: TMA zero fill
+      }
+      mbar_wait(&f_land[abuf], (par >> abuf) & 1u, 68);
+      par ^= 1u << abuf;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (m[j] == 0.f) {
+          const int r = tid + 64 * j;
+          uint8_t* px = sA + abuf * I5_A_BUF + (1 + (r >> 3)) * I5_PITCH + (1 + (r & 7)) * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<uint4*>(px + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(px + I5_A_PLANE + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) i5_arrive_cta_cluster(&a_masked[abuf], 0);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -685,7 +810,7 @@ int igemm_streamk_workspace(float** ws, unsigned int** flags, unsigned int* epoc
 unsigned long long* get_igemm_trace();                                                // tc_igemm_v2.cu
 
 template <int BN>
-static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep, const FusedTerm* ft, cudaStream_t st) {
   using Cfg = I5Cfg<BN>;
   IGemm5Params prm;
   int rc = igemm_streamk_workspace(&prm.ws, &prm.flags, &prm.epoch);
@@ -695,7 +820,9 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   prm.tiles_x = ceil_div(a.W, I5_TW);
   prm.tiles_m = prm.tiles_x * ceil_div(a.H, I5_TH);
   prm.tiles_n = b.N / BN;
-  prm.kchunks = b.K / 64;
+  prm.kreg = b.K / 64;
+  prm.kchunks = prm.kreg + (ft ? ft->f.C / 64 : 0);
+  prm.fmask = ft ? ft->rowmask : nullptr;
   prm.N = b.N;
   const long long pair_tiles = (long long)ceil_div(prm.tiles_m, 2) * prm.tiles_n;
   prm.total_units = pair_tiles * prm.kchunks * 9;
@@ -705,6 +832,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     const long long units = pair_tiles * prm.kchunks, g = std::min<long long>(74, units);
     const double mean = (double)units / (double)g;
     prm.align = ((double)((units + g - 1) / g) > 1.10 * mean) ? 1 : 9;
+    if (ft) prm.align = 9;      // a fused chunk works on its centre tap only: ranges must not start inside a halo unit
   }
   prm.ep = ep;
   // bf16 planes leave through shared memory + TMA; everything else (fp32 rows, masked copies, planar image gradient)
@@ -737,7 +865,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   }
   prm.knob = knob;
 
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo;
   {
     const uint64_t dims[3] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H};
     const uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2};
@@ -775,6 +903,27 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     tmO_hi = tmA_hi;      // never dereferenced
     tmO_lo = tmA_lo;
   }
+  if (ft) {
+    const uint64_t dims[3] = {(uint64_t)ft->f.C, (uint64_t)a.W, (uint64_t)a.H};
+    const uint64_t strides[2] = {(uint64_t)ft->f.C * 2, (uint64_t)a.W * ft->f.C * 2};
+    const uint32_t box[3] = {64u, (uint32_t)I5_HW, (uint32_t)I5_HR};
+    rc = make_tmap_bf16(&tmF_hi, ft->f.hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmF_lo, ft->f.lo, 3, dims, strides, box);
+    if (rc) return rc;
+    const uint64_t gdims[3] = {(uint64_t)ft->g.K, (uint64_t)ft->g.N, 1u};
+    const uint64_t gstrides[2] = {(uint64_t)ft->g.K * 2, (uint64_t)ft->g.N * ft->g.K * 2};
+    const uint32_t gbox[3] = {64u, (uint32_t)(BN / 2), 1u};
+    rc = make_tmap_bf16(&tmG_hi, ft->g.hi, 3, gdims, gstrides, gbox);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmG_lo, ft->g.lo, 3, gdims, gstrides, gbox);
+    if (rc) return rc;
+  } else {
+    tmF_hi = tmA_hi;      // never dereferenced
+    tmF_lo = tmA_lo;
+    tmG_hi = tmB_hi;
+    tmG_lo = tmB_lo;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SMB_CUDA_CHECK(cudaFuncSetAttribute(igemm_ph_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -788,20 +937,29 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     if (num_sms > 148) num_sms = 148;
   }
   const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units / prm.align));
-  SMB_LAUNCH(igemm_ph_kernel<BN>, (unsigned)(2 * pairs), I5_THREADS, Cfg::SMEM, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, prm);
+  const int threads = (prm.fmask && prm.kreg < prm.kchunks) ? I5_THREADS_MASK : I5_THREADS;
+  SMB_LAUNCH(igemm_ph_kernel<BN>, (unsigned)(2 * pairs), threads, Cfg::SMEM, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi,
+             tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo, prm);
   return SMB_OK;
 }
 
-int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
+int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st, const FusedTerm* ft) {
   SMB_REQUIRE(b.taps == 9, "igemm_ph: 3x3 convolutions only");
+  if (ft) {
+    SMB_REQUIRE(ft->f.H == a.H && ft->f.W == a.W && ft->f.C % 64 == 0 && ft->f.C > 0,
+                "igemm_ph: the fused term's features must have the conv's spatial size and a multiple of 64 channels");
+    SMB_REQUIRE(ft->g.taps == 1 && ft->g.N == b.N && ft->g.K == ft->f.C && b.N % 64 == 0,
+                "igemm_ph: the fused term's matrix must be [N=%d][K=%d]", b.N, ft->f.C);
+  }
   SMB_REQUIRE(a.C == b.K && b.K % 64 == 0 && (b.N % 64 == 0 || b.N == 16),
               "igemm_ph: K=%d must be a multiple of 64, N=%d a multiple of 64 (or the padded 16)", b.K, b.N);
-  SMB_REQUIRE((long long)ceil_div(a.W, I5_TW) * ceil_div(a.H, I5_TH) * ceil_div(b.N, 64) * (b.K / 64) * 9 < (1LL << 30),
+  SMB_REQUIRE((long long)ceil_div(a.W, I5_TW) * ceil_div(a.H, I5_TH) * ceil_div(b.N, 64) *
+                      (b.K / 64 + (ft ? ft->f.C / 64 : 0)) * 9 < (1LL << 30),
               "igemm_ph: problem too large for 32-bit work indices");
   if (a.pixels() == 0) return SMB_OK;
-  if (b.N == 16) return launch_igemm_ph_bn<16>(a, b, ep, st);
-  if (b.N % 128 == 0) return launch_igemm_ph_bn<128>(a, b, ep, st);
-  return launch_igemm_ph_bn<64>(a, b, ep, st);
+  if (b.N == 16) return launch_igemm_ph_bn<16>(a, b, ep, nullptr, st);
+  if (b.N % 128 == 0) return launch_igemm_ph_bn<128>(a, b, ep, ft, st);
+  return launch_igemm_ph_bn<64>(a, b, ep, ft, st);
 }
 
 }  // namespace smb

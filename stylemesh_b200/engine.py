@@ -285,6 +285,23 @@ def unit_conv3x3(impl: int, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.
     return y
 
 
+def unit_conv3x3_fused(x: torch.Tensor, w: torch.Tensor, f: torch.Tensor, g: torch.Tensor,
+                       rowmask: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv3x3(x, w) + rowmask * (g @ f) on the pair + halo kernel (the Gram backward folded into a data-gradient conv)."""
+    lib = _abi.load()
+    x = _require_cuda_f32(x, "x")
+    f = _require_cuda_f32(f, "f")
+    cout, cin = w.shape[0], w.shape[1]
+    _, H, W = x.shape
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    gc = g.detach().to("cpu", torch.float32).contiguous()
+    y = torch.empty((cout, H, W), device=x.device, dtype=torch.float32)
+    _abi.check(lib.smb_unit_conv3x3_fused(_abi.ptr(x), cin, H, W, _abi.ptr(wc), cout, _abi.ptr(f), _abi.ptr(gc),
+                                          _abi.ptr(rowmask), _abi.ptr(y), _abi.current_stream()),
+               "smb_unit_conv3x3_fused")
+    return y
+
+
 def unit_maxpool(x: torch.Tensor) -> torch.Tensor:
     lib = _abi.load()
     x = _require_cuda_f32(x, "x")

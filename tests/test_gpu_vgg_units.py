@@ -52,6 +52,32 @@ def test_conv3x3_data_gradient(impl, cin, cout, h, w):
     assert _rel(out, x.grad[0]) < 5e-5, _rel(out, x.grad[0])
 
 
+@pytest.mark.parametrize("masked", [False, True], ids=["nomask", "mask"])
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 64, 32, 40), (128, 128, 24, 32), (64, 128, 17, 23), (256, 256, 16, 16),
+                                          (512, 512, 30, 40), (64, 64, 120, 160), (128, 64, 33, 47)])
+def test_ph_conv_with_fused_gram_backward_term(cin, cout, h, w, masked):
+    """conv3x3(x) + m * (g f): the Gram backward (cs:74-80 through torch.bmm's backward) folded into the pair + halo
+    data-gradient conv as extra K-chunks; the mask zeroes feature pixels in shared memory."""
+    eng = _eng()
+    gen = torch.Generator().manual_seed(3 * cin + cout + h + int(masked))
+    x = torch.randn(cin, h, w, generator=gen) * 5
+    wt = torch.randn(cout, cin, 3, 3, generator=gen) * (2.0 / (9 * cin)) ** 0.5
+    f = F.relu(torch.randn(cout, h, w, generator=gen)) * 20
+    gm = torch.randn(cout, cout, generator=gen) / cout
+    gm = 0.5 * (gm + gm.t())
+    mask = (torch.rand(h * w, generator=gen) > 0.35).float() if masked else None
+    term = torch.einsum("nk,khw->nhw", gm.double(), f.double())
+    if masked:
+        term = term * mask.reshape(1, h, w).double()
+    ref = F.conv2d(x.unsqueeze(0).double(), wt.double(), None, padding=1)[0] + term
+    out = eng.unit_conv3x3_fused(x.cuda(), wt, f.cuda(), gm, None if mask is None else mask.cuda()).cpu()
+    assert _rel(out.double(), ref) < 5e-5, _rel(out.double(), ref)
+    if masked:      # masked pixels carry the plain convolution only
+        conv_only = F.conv2d(x.unsqueeze(0).double(), wt.double(), None, padding=1)[0]
+        sel = (mask == 0).reshape(h, w)
+        assert _rel(out.double()[:, sel], conv_only[:, sel]) < 5e-5
+
+
 @pytest.mark.parametrize("h,w", [(24, 32), (17, 23), (2, 2), (5, 3)])
 def test_maxpool_forward_backward(h, w):
     eng = _eng()
