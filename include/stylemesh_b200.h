@@ -76,6 +76,18 @@ int smb_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int smb_texreg_value(const float* param, int64_t n, float coef, float clamp_lo, float clamp_hi, float* out_accum,
                      void* stream);
 
+/* smb_adam_step / smb_texreg_value over ONE flat buffer holding all texture layers back to back
+ * (HierarchicalNeuralTexture.layers, texture.py:80-81), in a single launch each.  Segment l covers the elements
+ * [seg_begin[l], seg_begin[l+1]) (the last one ends at n) and has its own coefficient; seg_begin / seg_*coef are HOST
+ * arrays of num_segments (<= 8) entries, seg_begin[0] == 0, every offset a multiple of 4.  Padding elements between
+ * layers must be zero in all four buffers (they stay zero). */
+int smb_adam_step_segments(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* seg_begin, const float* seg_reg_coef, int num_segments, float lr, float beta1,
+                           float beta2, float eps, int step, float clamp_lo, float clamp_hi, float grad_scale,
+                           void* stream);
+int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_begin, const float* seg_coef,
+                              int num_segments, float clamp_lo, float clamp_hi, float* out_accum, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
  * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the

@@ -36,6 +36,8 @@ PROTOTYPES = [
     ("smb_uv_scatter_bwd", _i, [_pp, _ip, _ip, _i, _i, _p, _i, _i, _p, _p, _p, _p]),
     ("smb_adam_step", _i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i, _f, _f, _f, _f, _p]),
     ("smb_texreg_value", _i, [_p, _i64, _f, _f, _f, _p, _p]),
+    ("smb_adam_step_segments", _i, [_p, _p, _p, _p, _i64, _p, _p, _i, _f, _f, _f, _f, _i, _f, _f, _f, _p]),
+    ("smb_texreg_value_segments", _i, [_p, _i64, _p, _p, _i, _f, _f, _p, _p]),
     ("smb_ctx_create", _p, []),
     ("smb_ctx_destroy", None, [_p]),
     ("smb_ctx_set_impl", _i, [_p, _i, _i]),

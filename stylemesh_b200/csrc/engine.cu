@@ -415,6 +415,22 @@ int smb_texreg_value(const float* param, int64_t n, float coef, float clamp_lo, 
   return launch_sumsq_clamped(param, n, coef, clamp_lo, clamp_hi, out_accum, (cudaStream_t)stream);
 }
 
+int smb_adam_step_segments(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* seg_begin, const float* seg_reg_coef, int num_segments, float lr, float beta1,
+                           float beta2, float eps, int step, float clamp_lo, float clamp_hi, float grad_scale,
+                           void* stream) {
+  SMB_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0, "adam_step_segments: null argument");
+  return launch_adam_segments(param, grad, exp_avg, exp_avg_sq, n, seg_begin, seg_reg_coef, num_segments, lr, beta1,
+                              beta2, eps, step, clamp_lo, clamp_hi, grad_scale, (cudaStream_t)stream);
+}
+
+int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_begin, const float* seg_coef,
+                              int num_segments, float clamp_lo, float clamp_hi, float* out_accum, void* stream) {
+  SMB_REQUIRE(param && out_accum && n >= 0, "texreg_value_segments: null argument");
+  return launch_sumsq_segments(param, n, seg_begin, seg_coef, num_segments, clamp_lo, clamp_hi, out_accum,
+                               (cudaStream_t)stream);
+}
+
 // ---- context --------------------------------------------------------------------------------------------------
 smb_ctx* smb_ctx_create(void) {
   int dev = -1;

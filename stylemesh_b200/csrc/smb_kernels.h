@@ -34,6 +34,12 @@ int launch_adam(float* p, float* g, float* m, float* v, int64_t n, float lr, flo
                 int step, float clamp_lo, float clamp_hi, float reg_coef, float gscale, cudaStream_t st);
 int launch_sumsq_clamped(const float* x, int64_t n, float coef, float clamp_lo, float clamp_hi, float* out,
                          cudaStream_t st);
+// the two kernels above over a flat buffer of consecutive segments (host arrays seg_begin[num], coef[num]), one launch
+int launch_adam_segments(float* p, float* g, float* m, float* v, int64_t n, const int64_t* seg_begin,
+                         const float* seg_reg_coef, int num_segments, float lr, float beta1, float beta2, float eps,
+                         int step, float clamp_lo, float clamp_hi, float gscale, cudaStream_t st);
+int launch_sumsq_segments(const float* x, int64_t n, const int64_t* seg_begin, const float* seg_coef, int num_segments,
+                          float clamp_lo, float clamp_hi, float* out, cudaStream_t st);
 
 // ---- VGG side -----------------------------------------------------------------------------------------------
 // Activation planes (see smb_common.cuh): channels-last bf16 hi/lo pair.

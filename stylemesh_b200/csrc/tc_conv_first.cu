@@ -5,7 +5,11 @@
 // [128 pixels][K = 32 (27 + 5 zero)] bf16 hi/lo operand tiles directly in shared memory in the 128-byte-swizzled
 // K-major layout UMMA expects (generic-proxy stores + fence.proxy.async), one thread issues the 2 x 3 MMAs per tile
 // (N = 64, main/corr accumulators as in igemm_tc2), and four epilogue warps apply bias + ReLU and write the hi/lo
-// activation planes.  Persistent CTAs, double-buffered A tiles and TMEM accumulators: build(i+1) | MMA(i) | store(i-1).
+// activation planes.  Persistent CTAs, double-buffered TMEM accumulators: build(i+1) | MMA(i) | store(i-1); the A tile
+// is single-buffered (the producers hold tile i+1 in registers while the ~200-cycle MMAs of tile i drain it).
+// The planes leave through a swizzled shared-memory tile and one TMA tensor store per plane: per-thread 16-byte
+// stores at a 128-byte stride (32 L1 requests per instruction) made this kernel L1-throughput bound (ncu: L1/TEX 69 %,
+// DRAM 9 %, issue slots 28 % busy).
 #include "tc_common.cuh"
 #include "smb_epilogue.cuh"
 #include "smb_kernels.h"
@@ -19,7 +23,8 @@ constexpr int CF_N = 64;
 constexpr int CF_K = 32;                 // 27 real + 5 zero
 constexpr int CF_A_BYTES = CF_BM * 128;  // one plane: 128 rows x 128-byte swizzle rows (first 64 bytes carry K = 32)
 constexpr int CF_B_BYTES = CF_N * 128;
-constexpr int CF_SMEM = 2 * 2 * CF_A_BYTES + 2 * CF_B_BYTES + 1024 + 256;
+constexpr int CF_OUT_BYTES = CF_BM * 128; // one plane of the staged output tile: 128 pixels x 64 channels bf16
+constexpr int CF_SMEM = 2 * CF_A_BYTES + 2 * CF_B_BYTES + 2 * CF_OUT_BYTES + 1024 + 256;
 constexpr int CF_TMEM_COLS = 256;        // 2 buffers x (main 64 + corr 64)
 
 struct ConvFirstParams {
@@ -27,18 +32,22 @@ struct ConvFirstParams {
   const __nv_bfloat16* w_hi;             // [64][32] (k = ci*9 + r*3 + s, zero padded)
   const __nv_bfloat16* w_lo;
   int H, W, TH, TW, tiles_x, tiles;
+  int tma_out;                           // 1: hi/lo planes leave through shared memory + TMA tensor stores
   Epilogue ep;
 };
 
 // byte offset of 16-byte chunk `j` of row `r` inside a 1024-byte-aligned SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-__global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const ConvFirstParams prm) {
+__global__ void __launch_bounds__(CF_THREADS, 2)
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                     const ConvFirstParams prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                   // [buf][plane][CF_A_BYTES]
-  uint8_t* sB = smem + 4 * CF_A_BYTES;                  // [plane][CF_B_BYTES]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + 2 * CF_B_BYTES);   // [2] count 128 (producer threads)
+  uint8_t* sA = smem;                                   // [plane][CF_A_BYTES]
+  uint8_t* sB = smem + 2 * CF_A_BYTES;                  // [plane][CF_B_BYTES]
+  uint8_t* sOut = sB + 2 * CF_B_BYTES;                  // [plane][CF_OUT_BYTES]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sOut + 2 * CF_OUT_BYTES);   // [2] count 128 (producer threads)
   uint64_t* a_empty = a_full + 2;                       // [2] count 1 (tcgen05.commit)
   uint64_t* t_full = a_empty + 2;                       // [2] count 1 (tcgen05.commit)
   uint64_t* t_empty = t_full + 2;                       // [2] count 4 (epilogue warps)
@@ -54,6 +63,10 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
     *reinterpret_cast<uint4*>(sB + plane * CF_B_BYTES + sw128_off(n, j)) = v;
   }
   if (threadIdx.x == 0) {
+    if (prm.tma_out) {
+      tma_prefetch_desc(&tmO_hi);
+      tma_prefetch_desc(&tmO_lo);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&a_full[b], 128);
       mbar_init(&a_empty[b], 1);
@@ -78,8 +91,6 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
     const int r = threadIdx.x;             // 0..127
     int it = 0;
     for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
       const int y0 = (tile / prm.tiles_x) * prm.TH, x0 = (tile % prm.tiles_x) * prm.TW;
       const int y = y0 + r / prm.TW, x = x0 + r % prm.TW;
       float in[CF_K];
@@ -97,9 +108,9 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
                                            ? __ldg(prm.img + (int64_t)ci * P + (int64_t)yy * prm.W + xx)
                                            : 0.f;
           }
-      mbar_wait(&a_empty[buf], (use & 1u) ^ 1u, 41);        // the MMAs that read this buffer have completed
-      uint8_t* a_hi = sA + (buf * 2 + 0) * CF_A_BYTES;
-      uint8_t* a_lo = sA + (buf * 2 + 1) * CF_A_BYTES;
+      mbar_wait(&a_empty[0], ((uint32_t)it & 1u) ^ 1u, 41);  // the MMAs of the previous tile have read the buffer
+      uint8_t* a_hi = sA;
+      uint8_t* a_lo = sA + CF_A_BYTES;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 h, l;
@@ -111,7 +122,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
         *reinterpret_cast<uint4*>(a_lo + sw128_off(r, j)) = l;
       }
       fence_proxy_async_smem();            // generic-proxy stores -> visible to tcgen05 (async proxy)
-      mbar_arrive(&a_full[buf]);
+      mbar_arrive(&a_full[0]);
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
@@ -123,9 +134,9 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(&t_empty[buf], (use & 1u) ^ 1u, 42);
-        mbar_wait(&a_full[buf], use & 1u, 43);
+        mbar_wait(&a_full[0], (uint32_t)it & 1u, 43);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(sA + (buf * 2 + 0) * CF_A_BYTES), a_lo = a_hi + CF_A_BYTES;
+        const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + CF_A_BYTES;
         const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * CF_N), t_corr = t_main + CF_N;
 #pragma unroll
         for (int k = 0; k < CF_K / 16; ++k) {
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
           umma_f16(t_corr, dah, dbl, idesc, 1u);
           umma_f16(t_main, dah, dbh, idesc, (uint32_t)(k > 0));
         }
-        umma_commit(&a_empty[buf]);
+        umma_commit(&a_empty[0]);
         umma_commit(&t_full[buf]);
       }
     }
@@ -145,6 +156,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
     // ===================== epilogue: bias + ReLU + hi/lo planes =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const bool epi_leader = (warp == 5 && lane == 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < prm.tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -156,6 +168,10 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
       mbar_wait(&t_full[buf], use & 1u, 44);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * CF_N);
+      if (prm.tma_out) {                   // staging tile free once the previous tile's tensor stores have read it
+        if (epi_leader) bulk_wait_read0();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 #pragma unroll 1
       for (int c = 0; c < CF_N; c += 32) {
         uint32_t rm[32], rc[32];
@@ -167,14 +183,40 @@ __global__ void __launch_bounds__(CF_THREADS, 2) conv_first_tc_kernel(const Conv
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
-        if (valid) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
-          epilogue_store<32>(prm.ep, p, c, CF_N, v);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+        if (!prm.tma_out) {
+          if (valid) epilogue_store<32>(prm.ep, p, c, CF_N, v);
+          continue;
+        }
+        epilogue_apply<32>(prm.ep, p, c, CF_N, v, valid);
+        // pixel `row` = 128-byte row `row` of the staging tile; 16-byte chunk index XOR (row & 7) is the SWIZZLE_128B
+        // pattern of the tensor store (conflict free: 8 lanes cover 8 distinct chunks)
+        const uint32_t rbase = smem_u32(sOut) + (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 h, l;
+          split2_pack(v[8 * j], v[8 * j + 1], h.x, l.x);
+          split2_pack(v[8 * j + 2], v[8 * j + 3], h.y, l.y);
+          split2_pack(v[8 * j + 4], v[8 * j + 5], h.z, l.z);
+          split2_pack(v[8 * j + 6], v[8 * j + 7], h.w, l.w);
+          const uint32_t a = rbase + ((((uint32_t)(c >> 3) + (uint32_t)j) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + CF_OUT_BYTES), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w) : "memory");
+        }
+      }
+      if (prm.tma_out) {                   // one tensor store per plane; pixels outside the image are clipped by TMA
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (epi_leader) {
+          tma_store_3d(&tmO_hi, sOut, 0, x0, y0);
+          tma_store_3d(&tmO_lo, sOut + CF_OUT_BYTES, 0, x0, y0);
+          bulk_commit();
         }
       }
     }
+    if (prm.tma_out && epi_leader) bulk_wait_read0();   // shared memory may go once the stores have read it
   }
   tc_fence_before();
   __syncthreads();
@@ -208,13 +250,27 @@ int launch_conv_first_tc(const float* img, int H, int W, const __nv_bfloat16* w_
   prm.tiles = prm.tiles_x * ceil_div(H, prm.TH);
   prm.ep = ep_in;
   prm.ep.bias = bias;
+  const Epilogue& e = prm.ep;
+  prm.tma_out = (e.out_hi && e.out_lo && !e.out_f32 && !e.outm_hi && !e.out_planar3) ? 1 : 0;
+  CUtensorMap tmO_hi, tmO_lo;
+  memset(&tmO_hi, 0, sizeof(tmO_hi));
+  memset(&tmO_lo, 0, sizeof(tmO_lo));
+  if (prm.tma_out) {
+    const uint64_t dims[3] = {(uint64_t)CF_N, (uint64_t)W, (uint64_t)H};
+    const uint64_t strides[2] = {(uint64_t)CF_N * 2, (uint64_t)W * CF_N * 2};
+    const uint32_t box[3] = {64u, (uint32_t)prm.TW, (uint32_t)prm.TH};
+    int rc = make_tmap_bf16(&tmO_hi, e.out_hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmO_lo, e.out_lo, 3, dims, strides, box);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SMB_CUDA_CHECK(cudaFuncSetAttribute(conv_first_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM));
     attr_set = true;
   }
   const int grid = std::min(prm.tiles, 2 * 148);     // two CTAs per SM (83 KB smem, 256 TMEM columns each)
-  SMB_LAUNCH(conv_first_tc_kernel, grid, CF_THREADS, CF_SMEM, st, prm);
+  SMB_LAUNCH(conv_first_tc_kernel, grid, CF_THREADS, CF_SMEM, st, tmO_hi, tmO_lo, prm);
   return SMB_OK;
 }
 

@@ -170,23 +170,31 @@ struct GramTcParams {
   const float* rowmask;    // [P] of {0, 1} or nullptr: pixels with mask 0 do not contribute (cs:136-143 compaction)
 };
 
-template <int BN>
+// ALIAS: the whole Gram matrix is ONE tile (C == BN <= 128), so the A and the B operand are the same channels of the
+// same pixels: the stage holds them once and both descriptors point at it.  The r11 / r21 Grams are HBM-bound
+// reductions; with separate A / B copies (and the duplicated upper half of A at C = 64) every feature byte crossed
+// L2 -> shared memory three times and only a third of the bytes in flight were useful.
+template <int BN, bool ALIAS>
 struct GramCfg {
-  static constexpr int A_BYTES = 2 * GR_BOX_BYTES;            // 128 channels
-  static constexpr int B_BYTES = (BN / 64) * GR_BOX_BYTES;
+  static constexpr int A_BYTES = ALIAS ? (BN / 64) * GR_BOX_BYTES : 2 * GR_BOX_BYTES;   // per plane (non-alias: 128 ch)
+  static constexpr int B_BYTES = ALIAS ? 0 : (BN / 64) * GR_BOX_BYTES;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES < 8 ? TC_SMEM_BUDGET / STAGE_BYTES : 8;
+  // C == 64 runs the M = 128 MMA with rows 64..127 of A read from the 8 KiB after the tile (results dropped): the last
+  // stage's lo plane needs that much readable shared memory behind it
+  static constexpr int SLACK = (ALIAS && BN == 64) ? GR_BOX_BYTES : 0;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + SLACK + TC_SMEM_EXTRA;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN>
+template <int BN, bool ALIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const GramTcParams prm) {
-  using Cfg = GramCfg<BN>;
+  using Cfg = GramCfg<BN, ALIAS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::SLACK);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
   uint64_t* masked_bar = tmem_full_bar + 1;              // [STAGES] count 128: masked pixel rows of B are zeroed
@@ -231,15 +239,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int pix = (int)(pbeg + (int64_t)it * GR_KP);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < Cfg::A_BYTES / GR_BOX_BYTES; ++g) {
           const int ch = i0 + ((g < a_groups) ? g * 64 : 0);
           tma_load_2d(st + g * GR_BOX_BYTES, &tm_hi, &full_bar[stage], ch, pix);
           tma_load_2d(st + Cfg::A_BYTES + g * GR_BOX_BYTES, &tm_lo, &full_bar[stage], ch, pix);
         }
-        for (int g = 0; g < BN / 64; ++g) {
-          tma_load_2d(st + 2 * Cfg::A_BYTES + g * GR_BOX_BYTES, &tm_hi, &full_bar[stage], j0 + g * 64, pix);
-          tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + g * GR_BOX_BYTES, &tm_lo, &full_bar[stage], j0 + g * 64,
-                      pix);
+        if constexpr (!ALIAS) {
+          for (int g = 0; g < BN / 64; ++g) {
+            tma_load_2d(st + 2 * Cfg::A_BYTES + g * GR_BOX_BYTES, &tm_hi, &full_bar[stage], j0 + g * 64, pix);
+            tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + g * GR_BOX_BYTES, &tm_lo, &full_bar[stage], j0 + g * 64,
+                        pix);
+          }
         }
       }
     }
@@ -253,8 +263,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
-        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+        const uint32_t b_hi = ALIAS ? a_hi : a_hi + 2 * Cfg::A_BYTES;
+        const uint32_t b_lo = ALIAS ? a_lo : b_hi + Cfg::B_BYTES;
 #pragma unroll
         for (int k = 0; k < GR_KP / 16; ++k) {
           // MN-major SWIZZLE_128B: 64-channel groups GR_BOX_BYTES apart (LBO), 8-pixel groups 1024 B apart (SBO),
@@ -292,7 +302,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
         mbar_wait(&full_bar[stage], phase, 14);
         if (m == 0.f) {
-          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + plane * Cfg::B_BYTES + pl * 128;
+          // (ALIAS: A and B are the same bytes - zeroing the pixel in both operands is still m_p, m in {0,1})
+          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + pl * 128 +
+                          (ALIAS ? plane * Cfg::A_BYTES : 2 * Cfg::A_BYTES + plane * Cfg::B_BYTES);
 #pragma unroll
           for (int g = 0; g < BN / 64; ++g)
 #pragma unroll
@@ -413,9 +425,9 @@ int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStre
   return launch_igemm_tc_bn<64>(a, b, ep, st);
 }
 
-template <int BN>
+template <int BN, bool ALIAS>
 static int launch_gram_tc_bn(const Act& fm, const float* rowmask, float* partial, int nsplit, cudaStream_t st) {
-  using Cfg = GramCfg<BN>;
+  using Cfg = GramCfg<BN, ALIAS>;
   GramTcParams prm;
   prm.C = fm.C;
   prm.nsplit = nsplit;
@@ -431,14 +443,14 @@ static int launch_gram_tc_bn(const Act& fm, const float* rowmask, float* partial
   if (rc) return rc;
   rc = make_tmap_bf16(&tm_lo, fm.lo, 2, dims, strides, box);
   if (rc) return rc;
-  const int smem_bytes = Cfg::STAGES * Cfg::STAGE_BYTES + TC_SMEM_EXTRA;
+  const int smem_bytes = Cfg::SMEM;
   static bool attr_set = false;
   if (!attr_set) {
-    SMB_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SMB_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel<BN, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   dim3 grid(ceil_div(fm.C, TC_BM), fm.C / BN, nsplit);
-  SMB_LAUNCH(gram_tc_kernel<BN>, grid, TC_THREADS, smem_bytes, st, tm_hi, tm_lo, prm);
+  SMB_LAUNCH((gram_tc_kernel<BN, ALIAS>), grid, TC_THREADS, smem_bytes, st, tm_hi, tm_lo, prm);
   return SMB_OK;
 }
 
@@ -447,13 +459,14 @@ static int launch_gram_tc_bn(const Act& fm, const float* rowmask, float* partial
 // (C = 512, P = 4800) moved 39 MB of partials for a 9.8 MB feature map.  C >= 256 therefore uses BN = 64 (4x the
 // tiles, a quarter of the splits and of the partial bytes; the feature map is L2 resident, the tensor pipe is not
 // the limit at 2.5 GFLOP per layer).
-int gram_tc_bn(int C) { return (C >= 256 || C % 128 != 0) ? 64 : 128; }
+int gram_tc_bn(int C) { return C == 128 ? 128 : 64; }
 
 int launch_gram_tc(const Act& fm, const float* rowmask, float* partial, int nsplit, cudaStream_t st) {
   SMB_REQUIRE(fm.C % 64 == 0, "gram_tc: C=%d must be a multiple of 64", fm.C);
   SMB_REQUIRE(fm.pixels() > 0, "gram_tc: empty feature map");
-  if (gram_tc_bn(fm.C) == 128) return launch_gram_tc_bn<128>(fm, rowmask, partial, nsplit, st);
-  return launch_gram_tc_bn<64>(fm, rowmask, partial, nsplit, st);
+  if (fm.C == 128) return launch_gram_tc_bn<128, true>(fm, rowmask, partial, nsplit, st);
+  if (fm.C == 64) return launch_gram_tc_bn<64, true>(fm, rowmask, partial, nsplit, st);
+  return launch_gram_tc_bn<64, false>(fm, rowmask, partial, nsplit, st);
 }
 
 }  // namespace smb

@@ -107,6 +107,38 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, reg
     _abi.check(rc, "smb_adam_step")
 
 
+def _segment_arrays(seg_begin, seg_coef):
+    import ctypes as C
+    n = len(seg_begin)
+    if n != len(seg_coef) or n < 1:
+        raise ValueError("segment offsets and coefficients must have the same non-zero length")
+    return (C.c_int64 * n)(*[int(b) for b in seg_begin]), (C.c_float * n)(*[float(c) for c in seg_coef]), n
+
+
+def adam_step_segments(param, grad, exp_avg, exp_avg_sq, seg_begin, seg_reg_coef, lr, beta1, beta2, eps, step,
+                       grad_scale=1.0, clamp=(CLAMP_LO, CLAMP_HI)) -> None:
+    """adam_step over a flat buffer of consecutive layers (segment l starts at seg_begin[l]) in one launch."""
+    lib = _abi.load()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("adam_step_segments operates in place on contiguous CUDA float32 tensors")
+    begin, coef, n = _segment_arrays(seg_begin, seg_reg_coef)
+    rc = lib.smb_adam_step_segments(_abi.ptr(param), _abi.ptr(grad), _abi.ptr(exp_avg), _abi.ptr(exp_avg_sq),
+                                    param.numel(), begin, coef, n, lr, beta1, beta2, eps, int(step), clamp[0], clamp[1],
+                                    grad_scale, _abi.current_stream())
+    _abi.check(rc, "smb_adam_step_segments")
+
+
+def texreg_value_segments(param: torch.Tensor, seg_begin, seg_coef, out_accum: torch.Tensor,
+                          clamp=(CLAMP_LO, CLAMP_HI)) -> None:
+    """out_accum += sum_l seg_coef[l] * sum(clamp(segment l)^2) in one launch."""
+    lib = _abi.load()
+    begin, coef, n = _segment_arrays(seg_begin, seg_coef)
+    rc = lib.smb_texreg_value_segments(_abi.ptr(param), param.numel(), begin, coef, n, clamp[0], clamp[1],
+                                       _abi.ptr(out_accum), _abi.current_stream())
+    _abi.check(rc, "smb_texreg_value_segments")
+
+
 def launch_count() -> int:
     """kernel launches issued by libstylemesh_b200.so in this process so far."""
     return int(_abi.load().smb_launch_count())

@@ -37,7 +37,7 @@ class _GradAlreadyDeposited(torch.autograd.Function):
 
 class FusedTextureAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) for the texture layers (model.py:391-395)
-    as ONE fused kernel per layer that also applies the clamp of NeuralTexture.normalize(), adds the regulariser
+    as ONE fused kernel over all layers that also applies the clamp of NeuralTexture.normalize(), adds the regulariser
     gradient, scales by 1/world_size after the all-reduce and zeroes the gradient buffer for the next step."""
 
     def __init__(self, pipeline, params, lr):
@@ -60,10 +60,10 @@ class FusedTextureAdam(torch.optim.Optimizer):
                 torch.distributed.all_reduce(st["grad"])          # one collective per step over NVLink
         group = self.param_groups[0]
         b1, b2 = group["betas"]
-        for l, (a, b) in enumerate(st["spans"]):
-            _eng.adam_step(st["param"][a:b], st["grad"][a:b], st["exp_avg"][a:b], st["exp_avg_sq"][a:b],
-                           group["lr"], b1, b2, group["eps"], self._steps, reg_coef=pl._reg_grad_coef(l),
-                           grad_scale=1.0 / world)
+        spans = st["spans"]             # all layers in one launch: the flat buffers are contiguous, padding stays 0
+        _eng.adam_step_segments(st["param"], st["grad"], st["exp_avg"], st["exp_avg_sq"], [a for a, _ in spans],
+                                [pl._reg_grad_coef(l) for l in range(len(spans))], group["lr"], b1, b2, group["eps"],
+                                self._steps, grad_scale=1.0 / world)
         return None
 
 
@@ -298,10 +298,11 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
             gl = self._grad_tensors()
             for j, i in enumerate(keep):
                 _eng.uv_scatter_bwd(gl, uvs[i][0], grads[j], vp["hook0"].get(i), vp["hook1"][i])
-        for l, m in enumerate(self._layer_modules()):                                    # model.py:264-267
-            wl = self._reg_weight(l)
-            if wl > 0:
-                _eng.texreg_value(m.data.detach(), wl / m.data.numel(), buf[2:3])
+        mods = self._layer_modules()                                                     # model.py:264-267
+        reg = [self._reg_weight(l) / m.data.numel() for l, m in enumerate(mods)]
+        if any(c > 0 for c in reg):
+            st = self._ensure_fused_state()
+            _eng.texreg_value_segments(st["param"], [a for a, _ in st["spans"]], reg, buf[2:3])
         torch.sum(buf[0:3], dim=0, keepdim=True, out=buf[3:4])                           # model.py:270
         return buf
 

@@ -48,6 +48,22 @@ def texreg_value(param, coef, out_accum, clamp=CLAMP):
     out_accum += coef * (param.clamp(*clamp) ** 2).sum()
 
 
+def _segment_ends(param, seg_begin):
+    return list(seg_begin[1:]) + [param.numel()]
+
+
+def adam_step_segments(param, grad, exp_avg, exp_avg_sq, seg_begin, seg_reg_coef, lr, beta1, beta2, eps, step,
+                       grad_scale=1.0, clamp=CLAMP):
+    for a, b, c in zip(seg_begin, _segment_ends(param, seg_begin), seg_reg_coef):
+        adam_step(param[a:b], grad[a:b], exp_avg[a:b], exp_avg_sq[a:b], lr, beta1, beta2, eps, step, reg_coef=c,
+                  grad_scale=grad_scale, clamp=clamp)
+
+
+def texreg_value_segments(param, seg_begin, seg_coef, out_accum, clamp=CLAMP):
+    for a, b, c in zip(seg_begin, _segment_ends(param, seg_begin), seg_coef):
+        texreg_value(param[a:b], c, out_accum, clamp)
+
+
 def unit_gram(impl, f, rowmask, inv_n):
     fl = f.reshape(f.shape[0], -1)
     if rowmask is not None:
@@ -150,6 +166,7 @@ def install(monkeypatch):
     """Route the product's engine calls to the emulation (tests only)."""
     from stylemesh_b200 import engine
     from stylemesh_b200.model import model as pm
-    for name in ["uv_sample_fwd", "uv_scatter_bwd", "adam_step", "texreg_value", "unit_gram", "VGGEngine"]:
+    for name in ["uv_sample_fwd", "uv_scatter_bwd", "adam_step", "texreg_value", "adam_step_segments",
+                 "texreg_value_segments", "unit_gram", "VGGEngine"]:
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "require_cuda_device", lambda dev: None)

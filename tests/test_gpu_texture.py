@@ -118,3 +118,45 @@ def test_texreg_value():
     acc = torch.zeros(1, device="cuda")
     eng.texreg_value(x.cuda(), 7.0 / x.numel(), acc)
     assert abs(float(acc) - float(want)) <= 1e-5 * float(want)
+
+
+def test_segmented_adam_and_texreg_equal_the_per_layer_kernels():
+    """One launch over the flat 4-layer buffer (64-float aligned segments with zero padding) == one launch per layer,
+    bit for bit: same arithmetic per element, only the regulariser coefficient is looked up per segment."""
+    eng = _eng()
+    g = torch.Generator().manual_seed(21)
+    sizes = [3 * 40 * 40, 3 * 20 * 20, 3 * 10 * 10, 3 * 5 * 5]
+    begin, off = [], 0
+    for n in sizes:
+        begin.append(off)
+        off += (n + 63) // 64 * 64
+    coefs = [2.0 * 5e3 * w / n for w, n in zip([8.0, 4.0, 2.0, 0.0], sizes)]
+
+    def fresh():
+        p = torch.zeros(off)
+        gr = torch.zeros(off)
+        for a, n in zip(begin, sizes):
+            p[a:a + n] = torch.rand(n, generator=torch.Generator().manual_seed(a)) * 400 - 200
+            gr[a:a + n] = torch.randn(n, generator=torch.Generator().manual_seed(a + 1))
+        return p.cuda(), gr.cuda(), torch.zeros(off, device="cuda"), torch.zeros(off, device="cuda")
+
+    p1, g1, m1, v1 = fresh()
+    p2, g2, m2, v2 = fresh()
+    acc1, acc2 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    for step in (1, 2, 3):
+        eng.texreg_value_segments(p1, begin, [c / 2.0 for c in coefs], acc1)
+        eng.adam_step_segments(p1, g1, m1, v1, begin, coefs, 1.0, 0.9, 0.999, 1e-8, step, grad_scale=0.5)
+        for a, n, c in zip(begin, sizes, coefs):
+            eng.texreg_value(p2[a:a + n], c / 2.0, acc2)
+            eng.adam_step(p2[a:a + n], g2[a:a + n], m2[a:a + n], v2[a:a + n], 1.0, 0.9, 0.999, 1e-8, step,
+                          reg_coef=c, grad_scale=0.5)
+        assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+        assert float(g1.abs().max()) == 0.0
+        g1.copy_(torch.randn(off, generator=g).cuda() * (g2 * 0 + 1))
+        g2.copy_(g1)
+        for a, n in zip(begin, sizes):                     # padding carries no gradient
+            g1[a + n:a + (n + 63) // 64 * 64] = 0
+            g2[a + n:a + (n + 63) // 64 * 64] = 0
+    for a, n in zip(begin, sizes):                         # padding stayed exactly zero
+        assert float(p1[a + n:a + (n + 63) // 64 * 64].abs().max() if (n % 64) else 0.0) == 0.0
+    assert abs(float(acc1) - float(acc2)) <= 1e-5 * abs(float(acc2))

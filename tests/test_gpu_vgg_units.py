@@ -110,3 +110,21 @@ def test_masked_gram(impl, c, h, w, masked):
     out = eng.unit_gram(impl, f.cuda(), None if mask is None else mask.cuda(), 1.0 / n).cpu()
     assert _rel(out.double(), ref) < 2e-5, _rel(out.double(), ref)
     assert torch.allclose(out, out.t(), rtol=1e-5, atol=1e-5 * float(out.abs().max()))     # symmetry property
+
+
+@pytest.mark.parametrize("h,w", [(37, 53), (64, 128), (48, 200), (17, 16)])
+def test_first_layer_tcgen05_ragged_sizes(h, w, tmp_path):
+    """conv1_1 (3 -> 64, software im2col + TMA-store epilogue): image sizes that do not divide the 128-pixel patch, so
+    the tensor store has to clip rows / columns (cs:49 relu(conv1_1(x)))."""
+    from stylemesh_b200 import synthetic as syn
+    from stylemesh_b200.model.losses.content_and_style_losses import VGG
+    sd = syn.make_vgg_state_dict(3, bias_scale=0.5)
+    path = str(tmp_path / "vgg.pth")
+    torch.save(sd, path)
+    vgg = VGG(model_path=path).cuda()
+    g = torch.Generator().manual_seed(h * w)
+    x = torch.rand(1, 3, h, w, generator=g) * 255 - 110
+    got = vgg(x.cuda(), ["r11"])["r11"].cpu()
+    want = F.relu(F.conv2d(x, sd["conv1_1.weight"], sd["conv1_1.bias"], padding=1))
+    assert got.shape == want.shape
+    assert _rel(got, want) < 2e-5, _rel(got, want)
