@@ -171,6 +171,27 @@ def one_step(mdl, opt, batch, i):
     return out["loss"]
 
 
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, mean per launch, from the committed
+    `ncu --set full` summary (profiles/, written by tools/ncu_summary.py); (None, None) when there is none."""
+    import glob
+    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def to_bytes(txt):
+        val, unit = txt.split()[:2]
+        return float(val.replace(",", "")) * units[unit]
+
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*ncu_full*ph*.json")), reverse=True):
+        try:
+            rows = [r for r in json.load(open(path)) if "igemm_ph_kernel" in r.get("Kernel Name", "")]
+            tot = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows]
+            if tot:
+                return sum(tot) / len(tot), f"{os.path.basename(path)}: mean over {len(tot)} igemm_ph launches"
+        except Exception:
+            continue
+    return None, None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -218,7 +239,6 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -295,6 +315,9 @@ def run_ours(args):
         e2e = {"value": world * args.steps / (float(ems) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 16, "ms_per_step": float(ems) / args.steps}
 
+    # nvidia-smi sampled every 100 ms from the start of the value leg to the end of the e2e leg (all timed regions)
+    clocks = sampler.stop() if rank == 0 else None
+
     # ------------------------------------------------ roofline pass (per-kernel-class events) ------------------
     # (every rank runs these steps — optimizer.step() all-reduces — but only rank 0 reports)
     roof, kernel_ms = None, None
@@ -319,9 +342,10 @@ def run_ours(args):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic_per_launch()
         roof = {"kernel": "igemm_ph_kernel (VGG conv forward + data-gradient launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms,
                 "executed_bf16_tflops": 3.0 * achieved,
                 "note": "achieved = fp32-equivalent algorithmic FLOPs (2*P*Cout*Cin*9 per launch); each is executed "
