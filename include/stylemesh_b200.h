@@ -89,6 +89,48 @@ int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_
                               int num_segments, float clamp_lo, float clamp_hi, float* out_accum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * View preparation: the per-pixel work of Abstract_Dataset.__getitem__ (data/abstract_dataset.py:270-344) on the
+ * device, so that a scene's views can be prepared once and stay resident in HBM.  All
+ * pointers are device pointers unless marked HOST.  Resampling follows the libraries the reference calls (cv2.resize
+ * INTER_LINEAR / INTER_NEAREST, PIL NEAREST): the caller builds their index / weight tables on the host
+ * (stylemesh_b200/data/resample.py) and the kernels apply them, so indices are bit-exact by construction.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* get_uv_transform (model/texture/utils.py:87-91): grid = fl(fl(2 uv) - 1) of channels 0,1 of the renderer's
+ * (H,W,3) float32 map; optional calculate_mask (data/scannet_dataset.py:308-326): valid = (u != 0) | (v != 0),
+ * and (depth_at_uv > 0) when a depth map resampled to (H,W) is given (ScanNet; Matterport passes NULL). */
+int smb_view_uv_to_grid(const float* uv_hw3, int H, int W, float* grid_hw2, unsigned char* valid,
+                        const double* depth_at_uv, void* stream);
+
+/* dst[y][x] = src[ytab[y]][xtab[x]] for 1- or 4-byte elements (nearest resampling of the mask / angle map,
+ * data/abstract_dataset.py:306-311). */
+int smb_view_gather2d(const void* src, int elem_bytes, int Hs, int Ws, const int* ytab, const int* xtab, int Hd, int Wd,
+                      void* dst, void* stream);
+
+/* cv2.resize(depth, INTER_LINEAR) (data/abstract_dataset.py:301-304) into float64: src_type 0 = float64,
+ * 1 = float32 (rendered depth; float32 arithmetic), 2 = uint16 sensor depth divided by `divisor` (1000.0 ScanNet
+ * data/scannet_dataset.py:301, 4000.0 Matterport) in float64 first.  Same size in and out: conversion only. */
+int smb_view_resize_linear(const void* src, int src_type, double divisor, int Hs, int Ws, const int* yofs,
+                           const double* yalpha, const int* xofs, const double* xalpha, int Hd, int Wd, double* dst,
+                           void* stream);
+
+/* calculate_depth_level (data/scannet_dataset.py:328-366) in numpy's float64 arithmetic: continuous level (float32),
+ * nearest and second-nearest level (int64) and the interpolation weight of the nearest (float32) per pixel; also the
+ * float32 copy of the depth that transform_label produces (may be NULL).  levels: HOST array, ascending UV heights. */
+int smb_view_depth_levels(const double* depth, int64_t n, const double* levels, int num_levels, double min_depth,
+                          int depth_is_f32, float* depth_level, float* depth_f32, int64_t* rounded, int64_t* other,
+                          float* weight, void* stream);
+
+/* ToTensor + pre() (model/losses/rgb_transform.py:5-11): uint8 (H,W,3) RGB -> float32 (3,H,W) BGR, (x/255 - mean)*255. */
+int smb_view_rgb_pre(const unsigned char* rgb_hwc, int H, int W, float* out_chw, void* stream);
+
+/* angle_degrees = rad2deg(acos(cos_angle)) (data/abstract_dataset.py:338). */
+int smb_view_angle_degrees(const float* cos_angle, int64_t n, float* degrees, void* stream);
+
+/* erode of model/model.py:204-208: out = x where the zero-padded 3x3 box mean of x is exactly 1, else 0. */
+int smb_view_erode3x3(const float* x, int H, int W, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
  * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the
  * autograd backward of all of them).

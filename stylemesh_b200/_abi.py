@@ -25,6 +25,7 @@ _f = C.c_float
 _i = C.c_int
 _p = C.c_void_p
 _i64 = C.c_int64
+_d = C.c_double
 _pp = C.POINTER(C.c_void_p)
 _ip = C.POINTER(C.c_int)
 
@@ -38,6 +39,13 @@ PROTOTYPES = [
     ("smb_texreg_value", _i, [_p, _i64, _f, _f, _f, _p, _p]),
     ("smb_adam_step_segments", _i, [_p, _p, _p, _p, _i64, _p, _p, _i, _f, _f, _f, _f, _i, _f, _f, _f, _p]),
     ("smb_texreg_value_segments", _i, [_p, _i64, _p, _p, _i, _f, _f, _p, _p]),
+    ("smb_view_uv_to_grid", _i, [_p, _i, _i, _p, _p, _p, _p]),
+    ("smb_view_gather2d", _i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
+    ("smb_view_resize_linear", _i, [_p, _i, _d, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p]),
+    ("smb_view_depth_levels", _i, [_p, _i64, _p, _i, _d, _i, _p, _p, _p, _p, _p, _p]),
+    ("smb_view_rgb_pre", _i, [_p, _i, _i, _p, _p]),
+    ("smb_view_angle_degrees", _i, [_p, _i64, _p, _p]),
+    ("smb_view_erode3x3", _i, [_p, _i, _i, _p, _p]),
     ("smb_ctx_create", _p, []),
     ("smb_ctx_destroy", None, [_p]),
     ("smb_ctx_set_impl", _i, [_p, _i, _i]),

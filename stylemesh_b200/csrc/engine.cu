@@ -431,6 +431,54 @@ int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_
                                (cudaStream_t)stream);
 }
 
+// ---- view preparation ---------------------------------------------------------------------------------------------
+int smb_view_uv_to_grid(const float* uv_hw3, int H, int W, float* grid_hw2, unsigned char* valid,
+                        const double* depth_at_uv, void* stream) {
+  SMB_REQUIRE(uv_hw3 && grid_hw2 && H >= 0 && W >= 0, "view_uv_to_grid: bad argument");
+  SMB_REQUIRE(valid || !depth_at_uv, "view_uv_to_grid: a depth map without a mask output");
+  return launch_view_uv_grid(uv_hw3, H, W, grid_hw2, valid, depth_at_uv, (cudaStream_t)stream);
+}
+
+int smb_view_gather2d(const void* src, int elem_bytes, int Hs, int Ws, const int* ytab, const int* xtab, int Hd, int Wd,
+                      void* dst, void* stream) {
+  SMB_REQUIRE(src && ytab && xtab && dst && Hs > 0 && Ws > 0 && Hd >= 0 && Wd >= 0, "view_gather2d: bad argument");
+  return launch_view_gather2d(src, elem_bytes, Ws, ytab, xtab, Hd, Wd, dst, (cudaStream_t)stream);
+}
+
+int smb_view_resize_linear(const void* src, int src_type, double divisor, int Hs, int Ws, const int* yofs,
+                           const double* yalpha, const int* xofs, const double* xalpha, int Hd, int Wd, double* dst,
+                           void* stream) {
+  SMB_REQUIRE(src && dst && Hs > 0 && Ws > 0 && Hd >= 0 && Wd >= 0, "view_resize_linear: bad argument");
+  SMB_REQUIRE((Hs == Hd && Ws == Wd) || (yofs && yalpha && xofs && xalpha), "view_resize_linear: missing tables");
+  SMB_REQUIRE(src_type != 2 || divisor > 0.0, "view_resize_linear: uint16 input needs a positive divisor");
+  return launch_view_resize_linear(src, src_type, divisor, Hs, Ws, yofs, yalpha, xofs, xalpha, Hd, Wd, dst,
+                                   (cudaStream_t)stream);
+}
+
+int smb_view_depth_levels(const double* depth, int64_t n, const double* levels, int num_levels, double min_depth,
+                          int depth_is_f32, float* depth_level, float* depth_f32, int64_t* rounded, int64_t* other,
+                          float* weight, void* stream) {
+  SMB_REQUIRE(depth && levels && depth_level && rounded && other && weight && n >= 0, "view_depth_levels: null argument");
+  return launch_view_depth_levels(depth, n, levels, num_levels, min_depth, depth_is_f32, depth_level, depth_f32,
+                                  reinterpret_cast<long long*>(rounded), reinterpret_cast<long long*>(other), weight,
+                                  (cudaStream_t)stream);
+}
+
+int smb_view_rgb_pre(const unsigned char* rgb_hwc, int H, int W, float* out_chw, void* stream) {
+  SMB_REQUIRE(rgb_hwc && out_chw && H >= 0 && W >= 0, "view_rgb_pre: bad argument");
+  return launch_view_rgb_pre(rgb_hwc, H, W, out_chw, (cudaStream_t)stream);
+}
+
+int smb_view_angle_degrees(const float* cos_angle, int64_t n, float* degrees, void* stream) {
+  SMB_REQUIRE(cos_angle && degrees && n >= 0, "view_angle_degrees: bad argument");
+  return launch_view_angle_degrees(cos_angle, n, degrees, (cudaStream_t)stream);
+}
+
+int smb_view_erode3x3(const float* x, int H, int W, float* out, void* stream) {
+  SMB_REQUIRE(x && out && x != out && H >= 0 && W >= 0, "view_erode3x3: bad argument (in-place is not supported)");
+  return launch_view_erode3x3(x, H, W, out, (cudaStream_t)stream);
+}
+
 // ---- context --------------------------------------------------------------------------------------------------
 smb_ctx* smb_ctx_create(void) {
   int dev = -1;

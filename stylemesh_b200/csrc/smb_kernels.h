@@ -41,6 +41,21 @@ int launch_adam_segments(float* p, float* g, float* m, float* v, int64_t n, cons
 int launch_sumsq_segments(const float* x, int64_t n, const int64_t* seg_begin, const float* seg_coef, int num_segments,
                           float clamp_lo, float clamp_hi, float* out, cudaStream_t st);
 
+// ---- view preparation (view_prep_kernels.cu) ----------------------------------------------------------------------
+int launch_view_uv_grid(const float* uv3, int H, int W, float* grid2, unsigned char* valid, const double* depth,
+                        cudaStream_t st);
+int launch_view_gather2d(const void* src, int elem_bytes, int Ws, const int* ytab, const int* xtab, int Hd, int Wd,
+                         void* dst, cudaStream_t st);
+int launch_view_resize_linear(const void* src, int src_type, double divisor, int Hs, int Ws, const int* yofs,
+                              const double* ya, const int* xofs, const double* xa, int Hd, int Wd, double* dst,
+                              cudaStream_t st);
+int launch_view_depth_levels(const double* depth, int64_t n, const double* levels_host, int num_levels, double min_depth,
+                             int depth_is_f32, float* cont, float* depth_f32, long long* rounded, long long* other,
+                             float* weight, cudaStream_t st);
+int launch_view_rgb_pre(const unsigned char* hwc, int H, int W, float* chw, cudaStream_t st);
+int launch_view_angle_degrees(const float* c, int64_t n, float* deg, cudaStream_t st);
+int launch_view_erode3x3(const float* x, int H, int W, float* out, cudaStream_t st);
+
 // ---- VGG side -----------------------------------------------------------------------------------------------
 // Activation planes (see smb_common.cuh): channels-last bf16 hi/lo pair.
 struct Act {

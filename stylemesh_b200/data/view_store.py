@@ -1,0 +1,160 @@
+"""GPU-resident view store.
+
+The reference reads every view from disk again on every step: `Abstract_Dataset.__getitem__`
+(data/abstract_dataset.py:270-344) loads the colour image, the UV pyramid, the angle map and the depth map, resizes them
+with PIL / OpenCV on DataLoader workers, derives the validity mask and the depth-level maps in numpy and ships ~17 MB
+over PCIe — for views that repeat `index_repeat` (20-100) times per epoch.  A scene's views fit in a fraction of the
+B200's 180 GB, so here each view is uploaded ONCE as raw arrays, prepared by the `smb_view_*` kernels
+(csrc/view_prep_kernels.cu) and kept in HBM as the exact 13-tuple the pipeline consumes (model/model.py:183; the layout
+that torch's default_collate gives a batch of one).
+
+    store = ViewStore(device, levels=[256, 432, 608, 784], min_pyramid_depth=0.25, size_wh=(341, 256))
+    i = store.add(RawView(rgb=..., uv_pyramid=[...], angle=..., depth=..., depth_divisor=1000.0, ...))
+    batch = store[i]                       # 13-tuple of device tensors, no host work, no copy
+
+Resampling indices come from host-built tables (data/resample.py) that restate the libraries' conventions, so masks,
+depth levels and UV grids are bit-identical to the reference's (tests/test_gpu_view_store.py).  Decoding the colour
+JPEG and PIL's bicubic resize of it stay on the host (scene readers do both): file I/O, not arithmetic of the hot path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import engine as _eng
+from . import resample as _rs
+
+
+@dataclass
+class RawView:
+    """One view as the files hold it (after decoding; the colour image already resized to the working size)."""
+    rgb: np.ndarray                         # (H, W, 3) uint8, RGB, at the working size (PIL-resized by the reader)
+    uv_pyramid: List[np.ndarray]            # per kept level: (H_i, W_i, 3) float32 [u, v, mip LOD], invalid = (0, 0)
+    angle: np.ndarray                       # (Ha, Wa) or (Ha, Wa, C) float32, cos(theta) in channel 0
+    depth: np.ndarray                       # (Hd, Wd[, C]) uint16 sensor depth, float64 metres or float32 rendered depth
+    depth_divisor: float = 1.0              # uint16 -> metres (1000.0 ScanNet, 4000.0 Matterport)
+    extrinsics: np.ndarray = field(default_factory=lambda: np.identity(4, dtype=np.float32))
+    intrinsics: np.ndarray = field(default_factory=lambda: np.identity(4, dtype=np.float32))   # rescaled to the working size
+    index: Optional[int] = None             # dataset index (element 8 of the tuple); default: position in the store
+
+
+class ViewStore:
+    def __init__(self, device, levels: Sequence[float], min_pyramid_depth: float, size_wh: Tuple[int, int],
+                 mask_uses_depth: bool = True):
+        """levels: UV heights of the kept pyramid levels, ascending (`self.levels`, data/scannet_dataset.py:235);
+        size_wh: working (width, height) = the resolved `resize_size`; mask_uses_depth: ScanNet multiplies the validity
+        mask with depth > 0 (data/scannet_dataset.py:319-320), Matterport does not (data/matterport_dataset.py:304-307)."""
+        self.device = torch.device(device)
+        _eng.require_cuda_device(self.device)
+        self.levels = [float(l) for l in levels]
+        self.min_pyramid_depth = float(min_pyramid_depth)
+        self.size_wh = (int(size_wh[0]), int(size_wh[1]))
+        self.mask_uses_depth = bool(mask_uses_depth)
+        self._views: List[tuple] = []
+        self._tables: Dict[tuple, tuple] = {}
+        self.bytes_resident = 0
+
+    # ---- resampling tables, cached per (kind, source size, target size) -----------------------------------------
+    def _linear(self, src_hw, dst_hw):
+        key = ("lin", tuple(src_hw), tuple(dst_hw))
+        if key not in self._tables:
+            yo, ya = _rs.cv2_linear_table(src_hw[0], dst_hw[0])
+            xo, xa = _rs.cv2_linear_table(src_hw[1], dst_hw[1])
+            self._tables[key] = tuple(torch.from_numpy(t).to(self.device) for t in (yo, ya, xo, xa))
+        return self._tables[key]
+
+    def _nearest(self, kind, src_hw, dst_hw):
+        key = (kind, tuple(src_hw), tuple(dst_hw))
+        if key not in self._tables:
+            f = _rs.cv2_nearest_table if kind == "cv2" else _rs.pil_nearest_table
+            self._tables[key] = (torch.from_numpy(f(src_hw[0], dst_hw[0])).to(self.device),
+                                 torch.from_numpy(f(src_hw[1], dst_hw[1])).to(self.device))
+        return self._tables[key]
+
+    # ---- one view -------------------------------------------------------------------------------------------------
+    def add(self, raw: RawView) -> int:
+        """Upload the raw arrays of one view, run the preparation kernels, keep the 13-tuple resident."""
+        dev = self.device
+        W, H = self.size_wh
+        if len(raw.uv_pyramid) != len(self.levels):
+            raise ValueError(f"expected {len(self.levels)} UV pyramid levels, got {len(raw.uv_pyramid)}")
+        rgb = np.asarray(raw.rgb)
+        rgb = np.array(rgb, order="C", copy=not rgb.flags.writeable)
+        if rgb.dtype != np.uint8 or rgb.shape != (H, W, 3):
+            raise ValueError(f"rgb must be uint8 of shape {(H, W, 3)} (resized by the reader), got {rgb.dtype} {rgb.shape}")
+        depth = np.asarray(raw.depth)
+        if depth.ndim == 3:
+            depth = depth[:, :, 0]
+        depth = np.array(depth, order="C", copy=not depth.flags.writeable)      # PIL hands out read-only buffers
+        if depth.dtype not in (np.uint16, np.float64, np.float32):
+            raise ValueError(f"depth must be uint16, float64 or float32, got {depth.dtype}")
+        depth_is_f32 = depth.dtype == np.float32
+        divisor = float(raw.depth_divisor) if depth.dtype == np.uint16 else 1.0
+        angle = np.asarray(raw.angle)
+        if angle.ndim == 3:
+            angle = angle[:, :, 0]
+        angle = np.ascontiguousarray(angle, dtype=np.float32)
+
+        d_raw = torch.from_numpy(depth).to(dev)
+        # depth at the working size (abstract_dataset.py:301-304) -> depth tensor and the depth-level quadruple (:317)
+        tabs = None if depth.shape == (H, W) else self._linear(depth.shape, (H, W))
+        d_work = _eng.view_resize_linear(d_raw, (H, W), tabs, divisor)
+        level, depth32, rounded, other, weight = _eng.view_depth_levels(d_work, self.levels, self.min_pyramid_depth,
+                                                                        depth_is_f32)
+        # UV pyramid -> grids; the validity mask comes from the LAST level (abstract_dataset.py:283-285)
+        grids = []
+        mask_uv = None
+        for l, uv in enumerate(raw.uv_pyramid):
+            u = torch.from_numpy(np.ascontiguousarray(uv, dtype=np.float32)).to(dev)
+            last = l == len(raw.uv_pyramid) - 1
+            d_uv = None
+            if last and self.mask_uses_depth:
+                hw = tuple(u.shape[:2])
+                d_uv = _eng.view_resize_linear(d_raw, hw, None if depth.shape == hw else self._linear(depth.shape, hw),
+                                               divisor)
+            g, m = _eng.view_uv_to_grid(u, want_mask=last, depth_at_uv=d_uv)
+            grids.append(g.unsqueeze(0))
+            if last:
+                mask_uv = m
+        yt, xt = self._nearest("pil", tuple(mask_uv.shape), (H, W))                  # mask.resize(..., NEAREST) :311
+        mask = _eng.view_gather2d(mask_uv.to(torch.uint8), yt, xt).bool()
+        yt, xt = self._nearest("cv2", angle.shape, (H, W))                            # cv2 INTER_NEAREST :306-310
+        ang = _eng.view_gather2d(torch.from_numpy(angle).to(dev), yt, xt)
+        ang_deg = _eng.view_angle_degrees(ang)
+        rgb_t = _eng.view_rgb_pre(torch.from_numpy(rgb).to(dev))
+
+        idx = len(self._views) if raw.index is None else int(raw.index)
+        view = (rgb_t.unsqueeze(0),
+                torch.from_numpy(np.asarray(raw.extrinsics, dtype=np.float32)).to(dev).unsqueeze(0),
+                torch.from_numpy(np.asarray(raw.intrinsics, dtype=np.float32)).to(dev).unsqueeze(0),
+                depth32.reshape(1, 1, H, W), level.reshape(1, 1, H, W), rounded.reshape(1, 1, H, W),
+                other.reshape(1, 1, H, W), weight.reshape(1, 1, H, W),
+                torch.tensor([idx], dtype=torch.int64),                               # stays on the host: plan-cache key
+                grids, mask.unsqueeze(0), ang.reshape(1, 1, H, W), ang_deg.reshape(1, 1, H, W))
+        self._views.append(view)
+        self.bytes_resident += sum(t.numel() * t.element_size() for t in _tensors_of(view) if t.is_cuda)
+        return len(self._views) - 1
+
+    def extend(self, raws: Iterable[RawView]) -> List[int]:
+        return [self.add(r) for r in raws]
+
+    def __len__(self) -> int:
+        return len(self._views)
+
+    def __getitem__(self, i: int) -> tuple:
+        return self._views[i]
+
+    def batches(self, indices: Sequence[int], index_repeat: int = 1) -> List[tuple]:
+        """The order of RepeatingSampler (data/abstract_dataset.py:498-505): each index `index_repeat` times in a row."""
+        return [self._views[i] for i in indices for _ in range(max(1, int(index_repeat)))]
+
+
+def _tensors_of(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            yield from _tensors_of(o)

@@ -152,6 +152,112 @@ def texreg_value(param: torch.Tensor, coef: float, out_accum: torch.Tensor, clam
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# view preparation (data/abstract_dataset.py:270-344 on the device; used by stylemesh_b200.data.ViewStore)
+# ---------------------------------------------------------------------------------------------------------------
+def _require_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {dtype}")
+    return t
+
+
+def view_uv_to_grid(uv_hw3: torch.Tensor, want_mask: bool = False, depth_at_uv: Optional[torch.Tensor] = None):
+    """(H,W,3) renderer UV map -> grid (H,W,2) in [-1,1] and, optionally, the validity mask (H,W) bool."""
+    lib = _abi.load()
+    uv = _require_cuda(uv_hw3, torch.float32, "uv")
+    H, W, c = uv.shape
+    if c != 3:
+        raise ValueError("the renderer's UV maps have 3 channels (u, v, mip LOD)")
+    grid = torch.empty((H, W, 2), device=uv.device, dtype=torch.float32)
+    valid = torch.empty((H, W), device=uv.device, dtype=torch.uint8) if want_mask else None
+    if depth_at_uv is not None:
+        _require_cuda(depth_at_uv, torch.float64, "depth_at_uv")
+    _abi.check(lib.smb_view_uv_to_grid(_abi.ptr(uv), H, W, _abi.ptr(grid), _abi.ptr(valid), _abi.ptr(depth_at_uv),
+                                       _abi.current_stream()), "smb_view_uv_to_grid")
+    return grid, (valid.bool() if want_mask else None)
+
+
+def view_gather2d(src: torch.Tensor, ytab: torch.Tensor, xtab: torch.Tensor) -> torch.Tensor:
+    """dst[y][x] = src[ytab[y]][xtab[x]] (2-D, 1- or 4-byte elements; tables: CUDA int32)."""
+    lib = _abi.load()
+    if not (src.is_cuda and src.dim() == 2 and src.is_contiguous() and src.element_size() in (1, 4)):
+        raise ValueError("view_gather2d takes a contiguous 2-D CUDA tensor of 1- or 4-byte elements")
+    _require_cuda(ytab, torch.int32, "ytab")
+    _require_cuda(xtab, torch.int32, "xtab")
+    dst = torch.empty((ytab.numel(), xtab.numel()), device=src.device, dtype=src.dtype)
+    _abi.check(lib.smb_view_gather2d(_abi.ptr(src), src.element_size(), src.shape[0], src.shape[1], _abi.ptr(ytab),
+                                     _abi.ptr(xtab), dst.shape[0], dst.shape[1], _abi.ptr(dst), _abi.current_stream()),
+               "smb_view_gather2d")
+    return dst
+
+
+_DEPTH_TYPES = {torch.float64: 0, torch.float32: 1, torch.uint16: 2, torch.int16: 2}
+
+
+def view_resize_linear(src: torch.Tensor, out_hw, tables=None, divisor: float = 1.0) -> torch.Tensor:
+    """cv2 INTER_LINEAR of a 2-D depth map into float64; tables = (yofs, yalpha, xofs, xalpha) CUDA tensors built
+    by stylemesh_b200.data.resample (not needed when the size does not change)."""
+    lib = _abi.load()
+    if not (src.is_cuda and src.dim() == 2 and src.is_contiguous() and src.dtype in _DEPTH_TYPES):
+        raise ValueError("view_resize_linear takes a contiguous 2-D CUDA tensor (float64, float32 or uint16)")
+    Hd, Wd = int(out_hw[0]), int(out_hw[1])
+    same = (Hd, Wd) == tuple(src.shape)
+    if not same and tables is None:
+        raise ValueError("resampling tables are required when the size changes")
+    yo, ya, xo, xa = tables if tables is not None else (None, None, None, None)
+    dst = torch.empty((Hd, Wd), device=src.device, dtype=torch.float64)
+    _abi.check(lib.smb_view_resize_linear(_abi.ptr(src), _DEPTH_TYPES[src.dtype], float(divisor), src.shape[0],
+                                          src.shape[1], _abi.ptr(yo), _abi.ptr(ya), _abi.ptr(xo), _abi.ptr(xa), Hd, Wd,
+                                          _abi.ptr(dst), _abi.current_stream()), "smb_view_resize_linear")
+    return dst
+
+
+def view_depth_levels(depth: torch.Tensor, levels, min_depth: float, depth_is_f32: bool = False):
+    """-> (depth_level f32, depth f32, rounded i64, other i64, weight f32), each shaped like `depth` (float64)."""
+    import ctypes as C
+    lib = _abi.load()
+    d = _require_cuda(depth, torch.float64, "depth")
+    lv = (C.c_double * len(levels))(*[float(x) for x in levels])
+    outs = [torch.empty(d.shape, device=d.device, dtype=t)
+            for t in (torch.float32, torch.float32, torch.int64, torch.int64, torch.float32)]
+    _abi.check(lib.smb_view_depth_levels(_abi.ptr(d), d.numel(), lv, len(levels), float(min_depth), int(depth_is_f32),
+                                         _abi.ptr(outs[0]), _abi.ptr(outs[1]), _abi.ptr(outs[2]), _abi.ptr(outs[3]),
+                                         _abi.ptr(outs[4]), _abi.current_stream()), "smb_view_depth_levels")
+    return tuple(outs)
+
+
+def view_rgb_pre(rgb_hwc_u8: torch.Tensor) -> torch.Tensor:
+    lib = _abi.load()
+    x = _require_cuda(rgb_hwc_u8, torch.uint8, "rgb")
+    H, W, c = x.shape
+    if c != 3:
+        raise ValueError("rgb must be (H, W, 3) uint8")
+    out = torch.empty((3, H, W), device=x.device, dtype=torch.float32)
+    _abi.check(lib.smb_view_rgb_pre(_abi.ptr(x), H, W, _abi.ptr(out), _abi.current_stream()), "smb_view_rgb_pre")
+    return out
+
+
+def view_angle_degrees(cos_angle: torch.Tensor) -> torch.Tensor:
+    lib = _abi.load()
+    x = _require_cuda(cos_angle, torch.float32, "cos_angle")
+    out = torch.empty_like(x)
+    _abi.check(lib.smb_view_angle_degrees(_abi.ptr(x), x.numel(), _abi.ptr(out), _abi.current_stream()),
+               "smb_view_angle_degrees")
+    return out
+
+
+def view_erode3x3(x: torch.Tensor) -> torch.Tensor:
+    """model/model.py:204-208 on a (..., H, W) float32 map with at most one non-singleton leading dimension."""
+    lib = _abi.load()
+    x = _require_cuda(x, torch.float32, "x")
+    H, W = x.shape[-2], x.shape[-1]
+    if x.numel() != H * W:
+        raise ValueError("view_erode3x3 takes one (H, W) map (leading dimensions of size 1 are allowed)")
+    out = torch.empty_like(x)
+    _abi.check(lib.smb_view_erode3x3(_abi.ptr(x), H, W, _abi.ptr(out), _abi.current_stream()), "smb_view_erode3x3")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # VGG / loss engine
 # ---------------------------------------------------------------------------------------------------------------
 def _impl_from_env(name: str, default: int) -> int:

@@ -223,9 +223,8 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
     # ------------------------------------------------------------------------------------------------------
     @staticmethod
     def _erode(x):
-        k = torch.ones(1, 1, 3, 3, dtype=x.dtype, device=x.device)
-        e = torch.clamp(F.conv2d(x, k, padding=(1, 1)) / 9, 0, 1)
-        return x * (e == 1)
+        """model.py:204-208 — keep x where the zero-padded 3x3 box mean is exactly 1 (smb_view_erode3x3)."""
+        return _eng.view_erode3x3(x.to(torch.float32).contiguous())
 
     def build_view_plan(self, batch) -> dict:
         (rgb, _, _, _, _, rounded, other, interp_w, _, uvs, mask, angle_guidance, angle_degrees) = batch

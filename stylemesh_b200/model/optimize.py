@@ -1,11 +1,12 @@
 """CLI with the flag surface of the reference's `python -m model.optimize` (model/optimize.py:238-290), so that the
 scripts/train/optimize_texture_*.sh presets run unchanged on the B200 path.
 
-In scope: flag parsing, model construction, the training loop (lightning_shim.Trainer), texture export.
-Out of scope (SURVEY §2 #6,#9-#11): the ScanNet/Matterport file loaders and the post-run OpenGL mip-map render /
-video / LPIPS evaluation — `--dataset scannet|matterport` needs a DataModule factory registered with
-`register_datamodule` (the reference's data/ package can be plugged in there); `--dataset synthetic` generates
-seeded views in memory.
+In scope: flag parsing, model construction, the training loop (lightning_shim.Trainer), texture export, and
+`--dataset scannet`: one scene in the reference's directory layout, prepared once on the device and kept resident
+(stylemesh_b200/data).  `--dataset synthetic` generates seeded views in memory.
+Out of scope (SURVEY §2 #6,#9-#11): the Matterport house/region loader (register a DataModule factory with
+`register_datamodule`; its pixel work is covered by ViewStore(mask_uses_depth=False, depth_divisor=4000)) and the
+post-run OpenGL mip-map render / video / LPIPS evaluation.
 """
 from __future__ import annotations
 
@@ -85,6 +86,9 @@ def main(args):
         dm = SyntheticSceneDataModule(args)
     elif args.dataset in _DATAMODULES:
         dm = _DATAMODULES[args.dataset](args, {"rgb_pre": pre()})
+    elif args.dataset == "scannet":                    # optimize.py:44-63 on the GPU-resident view store
+        from ..data.scannet_scene import ScanNetViewStoreDataModule
+        dm = ScanNetViewStoreDataModule(args)
     else:
         raise ValueError(f"Unsupported dataset: {args.dataset} (file loaders are outside the B200 hot path; register "
                          f"one with stylemesh_b200.model.optimize.register_datamodule or use --dataset synthetic)")

@@ -64,6 +64,54 @@ def texreg_value_segments(param, seg_begin, seg_coef, out_accum, clamp=CLAMP):
         texreg_value(param[a:b], c, out_accum, clamp)
 
 
+# ---- view preparation: the numpy oracle behind the engine's view_* signatures (CPU host-logic tests only) -------------
+def view_uv_to_grid(uv_hw3, want_mask=False, depth_at_uv=None):
+    from oracle import view_prep_oracle as vo
+    uv = uv_hw3.numpy()
+    m = None
+    if want_mask:
+        m = (uv[:, :, 0] != 0) | (uv[:, :, 1] != 0)
+        if depth_at_uv is not None:
+            m = m & (depth_at_uv.numpy() > 0)
+        m = torch.from_numpy(m)
+    return torch.from_numpy(vo.uv_to_grid(uv)), m
+
+
+def view_gather2d(src, ytab, xtab):
+    return src[ytab.long()][:, xtab.long()]
+
+
+def view_resize_linear(src, out_hw, tables=None, divisor=1.0):
+    from oracle import view_prep_oracle as vo
+    a = src.numpy() if src.dtype != torch.uint16 else src.view(torch.int16).numpy().view("uint16")
+    if a.dtype == "uint16":
+        a = a / float(divisor)
+    return torch.from_numpy(vo.resize_linear_cv2(a, (int(out_hw[1]), int(out_hw[0]))).astype("float64"))
+
+
+def view_depth_levels(depth, levels, min_depth, depth_is_f32=False):
+    from oracle import view_prep_oracle as vo
+    d = depth.numpy().astype("float32") if depth_is_f32 else depth.numpy()
+    c, r, o, w = vo.depth_levels(d, levels, min_depth)
+    return (torch.from_numpy(c), depth.float(), torch.from_numpy(r), torch.from_numpy(o), torch.from_numpy(w))
+
+
+def view_rgb_pre(rgb):
+    from oracle import view_prep_oracle as vo
+    return torch.from_numpy(vo.rgb_pre(rgb.numpy()))
+
+
+def view_angle_degrees(c):
+    from oracle import view_prep_oracle as vo
+    return torch.from_numpy(vo.angle_degrees(c.numpy()))
+
+
+def view_erode3x3(x):
+    k = torch.ones(1, 1, 3, 3)
+    m = torch.clamp(F.conv2d(x.reshape(1, 1, x.shape[-2], x.shape[-1]), k, padding=1) / 9, 0, 1).reshape(x.shape)
+    return x * (m == 1)
+
+
 def unit_gram(impl, f, rowmask, inv_n):
     fl = f.reshape(f.shape[0], -1)
     if rowmask is not None:
@@ -167,6 +215,7 @@ def install(monkeypatch):
     from stylemesh_b200 import engine
     from stylemesh_b200.model import model as pm
     for name in ["uv_sample_fwd", "uv_scatter_bwd", "adam_step", "texreg_value", "adam_step_segments",
-                 "texreg_value_segments", "unit_gram", "VGGEngine"]:
+                 "texreg_value_segments", "unit_gram", "VGGEngine", "view_uv_to_grid", "view_gather2d",
+                 "view_resize_linear", "view_depth_levels", "view_rgb_pre", "view_angle_degrees", "view_erode3x3"]:
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "require_cuda_device", lambda dev: None)
