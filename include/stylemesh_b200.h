@@ -88,6 +88,21 @@ int smb_adam_step_segments(float* param, float* grad, float* exp_avg, float* exp
 int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_begin, const float* seg_coef,
                               int num_segments, float clamp_lo, float clamp_hi, float* out_accum, void* stream);
 
+/* Multi-GPU form of smb_adam_step_segments for view-sharded training (one process per GPU; replaces
+ * DistributedDataParallel's gradient all-reduce + torch.optim.Adam.step of the reference's `--gpus N` runs,
+ * model/optimize.py:30, model/model.py:395): reduce-scatter of the gradient, Adam on this rank's 1/world slice (the
+ * moments are sharded: only that slice of exp_avg / exp_avg_sq is used) and all-gather of the new texels, in one
+ * kernel over NVLink peer memory, followed by a kernel that zeroes the local gradient once every peer is done.
+ * grad_ptrs / param_ptrs / flag_ptrs: HOST arrays of `world` DEVICE pointers to every rank's flat gradient, flat
+ * parameter and flag buffer (own rank included; e.g. torch.distributed._symmetric_memory buffer_ptrs).  Flag buffers:
+ * at least 64 uint32, zero before the first call.  epoch: strictly increasing per call (the step counter); all ranks
+ * must issue the same sequence of calls.  The gradient is averaged over ranks (scale 1/world).  n: multiple of 4. */
+int smb_dist_adam_step(int rank, int world, float* const* grad_ptrs, float* const* param_ptrs,
+                       unsigned int* const* flag_ptrs, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const int64_t* seg_begin, const float* seg_reg_coef, int num_segments, float lr, float beta1,
+                       float beta2, float eps, int step, float clamp_lo, float clamp_hi, unsigned int epoch,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * View preparation: the per-pixel work of Abstract_Dataset.__getitem__ (data/abstract_dataset.py:270-344) on the
  * device, so that a scene's views can be prepared once and stay resident in HBM.  All

@@ -39,6 +39,7 @@ PROTOTYPES = [
     ("smb_texreg_value", _i, [_p, _i64, _f, _f, _f, _p, _p]),
     ("smb_adam_step_segments", _i, [_p, _p, _p, _p, _i64, _p, _p, _i, _f, _f, _f, _f, _i, _f, _f, _f, _p]),
     ("smb_texreg_value_segments", _i, [_p, _i64, _p, _p, _i, _f, _f, _p, _p]),
+    ("smb_dist_adam_step", _i, [_i, _i, _p, _p, _p, _p, _p, _i64, _p, _p, _i, _f, _f, _f, _f, _i, _f, _f, C.c_uint, _p]),
     ("smb_view_uv_to_grid", _i, [_p, _i, _i, _p, _p, _p, _p]),
     ("smb_view_gather2d", _i, [_p, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     ("smb_view_resize_linear", _i, [_p, _i, _d, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p]),

@@ -431,6 +431,16 @@ int smb_texreg_value_segments(const float* param, int64_t n, const int64_t* seg_
                                (cudaStream_t)stream);
 }
 
+int smb_dist_adam_step(int rank, int world, float* const* grad_ptrs, float* const* param_ptrs,
+                       unsigned int* const* flag_ptrs, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const int64_t* seg_begin, const float* seg_reg_coef, int num_segments, float lr, float beta1,
+                       float beta2, float eps, int step, float clamp_lo, float clamp_hi, unsigned int epoch,
+                       void* stream) {
+  SMB_REQUIRE(grad_ptrs && param_ptrs && flag_ptrs && exp_avg && exp_avg_sq, "dist_adam_step: null argument");
+  return launch_dist_adam(rank, world, grad_ptrs, param_ptrs, flag_ptrs, exp_avg, exp_avg_sq, n, seg_begin, seg_reg_coef,
+                          num_segments, lr, beta1, beta2, eps, step, clamp_lo, clamp_hi, epoch, (cudaStream_t)stream);
+}
+
 // ---- view preparation ---------------------------------------------------------------------------------------------
 int smb_view_uv_to_grid(const float* uv_hw3, int H, int W, float* grid_hw2, unsigned char* valid,
                         const double* depth_at_uv, void* stream) {

@@ -40,6 +40,12 @@ int launch_adam_segments(float* p, float* g, float* m, float* v, int64_t n, cons
                          int step, float clamp_lo, float clamp_hi, float gscale, cudaStream_t st);
 int launch_sumsq_segments(const float* x, int64_t n, const int64_t* seg_begin, const float* seg_coef, int num_segments,
                           float clamp_lo, float clamp_hi, float* out, cudaStream_t st);
+// N > 1: gradient reduce-scatter + Adam on this rank's slice + parameter all-gather over peer memory (HOST arrays of
+// `world` device pointers: every rank's gradient / parameter / flag buffers, own rank included)
+int launch_dist_adam(int rank, int world, float* const* grad_ptrs, float* const* param_ptrs,
+                     unsigned int* const* flag_ptrs, float* m, float* v, int64_t n, const int64_t* seg_begin,
+                     const float* seg_reg_coef, int num_segments, float lr, float beta1, float beta2, float eps,
+                     int step, float clamp_lo, float clamp_hi, unsigned int epoch, cudaStream_t st);
 
 // ---- view preparation (view_prep_kernels.cu) ----------------------------------------------------------------------
 int launch_view_uv_grid(const float* uv3, int H, int W, float* grid2, unsigned char* valid, const double* depth,

@@ -129,6 +129,25 @@ def adam_step_segments(param, grad, exp_avg, exp_avg_sq, seg_begin, seg_reg_coef
     _abi.check(rc, "smb_adam_step_segments")
 
 
+def dist_adam_step(rank: int, world: int, grad_ptrs, param_ptrs, flag_ptrs, exp_avg, exp_avg_sq, numel: int, seg_begin,
+                   seg_reg_coef, lr, beta1, beta2, eps, step, epoch: int, clamp=(CLAMP_LO, CLAMP_HI)) -> None:
+    """Gradient reduce-scatter + Adam on this rank's slice + parameter all-gather over peer memory (one kernel) and
+    the local gradient reset; *_ptrs are lists of `world` device addresses (every rank's buffer, own included)."""
+    import ctypes as C
+    lib = _abi.load()
+    if not (len(grad_ptrs) == len(param_ptrs) == len(flag_ptrs) == world):
+        raise ValueError("need one gradient / parameter / flag pointer per rank")
+    for t in (exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == numel):
+            raise ValueError("dist_adam_step: the moment buffers must be contiguous CUDA float32 of the flat size")
+    arr = lambda ps: (C.c_void_p * world)(*[int(p) for p in ps])
+    begin, coef, n = _segment_arrays(seg_begin, seg_reg_coef)
+    rc = lib.smb_dist_adam_step(int(rank), int(world), arr(grad_ptrs), arr(param_ptrs), arr(flag_ptrs),
+                                _abi.ptr(exp_avg), _abi.ptr(exp_avg_sq), int(numel), begin, coef, n, lr, beta1, beta2,
+                                eps, int(step), clamp[0], clamp[1], int(epoch) & 0xFFFFFFFF, _abi.current_stream())
+    _abi.check(rc, "smb_dist_adam_step")
+
+
 def texreg_value_segments(param: torch.Tensor, seg_begin, seg_coef, out_accum: torch.Tensor,
                           clamp=(CLAMP_LO, CLAMP_HI)) -> None:
     """out_accum += sum_l seg_coef[l] * sum(clamp(segment l)^2) in one launch."""

@@ -53,14 +53,24 @@ class FusedTextureAdam(torch.optim.Optimizer):
         pl = self._pipeline
         st = pl._ensure_fused_state()
         self._steps += 1
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            if world > 1:
-                torch.distributed.all_reduce(st["grad"])          # one collective per step over NVLink
         group = self.param_groups[0]
         b1, b2 = group["betas"]
         spans = st["spans"]             # all layers in one launch: the flat buffers are contiguous, padding stays 0
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1 and st.get("peer"):
+                # the one exchange of the step fused with the optimiser: reduce-scatter of the gradient,
+                # Adam on this rank's slice (sharded moments), all-gather of the new texels - one kernel over NVLink
+                pr = st["peer"]["ptrs"]
+                st["peer"]["epoch"] = st["peer"].get("epoch", 0) + 1      # monotonic for the life of the flag buffers
+                _eng.dist_adam_step(torch.distributed.get_rank(), world, pr["grad"], pr["param"], pr["flags"],
+                                    st["exp_avg"], st["exp_avg_sq"], st["param"].numel(), [a for a, _ in spans],
+                                    [pl._reg_grad_coef(l) for l in range(len(spans))], group["lr"], b1, b2,
+                                    group["eps"], self._steps, epoch=st["peer"]["epoch"])
+                return None
+            if world > 1:
+                torch.distributed.all_reduce(st["grad"])          # fallback: NCCL all-reduce, then the local Adam
         _eng.adam_step_segments(st["param"], st["grad"], st["exp_avg"], st["exp_avg_sq"], [a for a, _ in spans],
                                 [pl._reg_grad_coef(l) for l in range(len(spans))], group["lr"], b1, b2, group["eps"],
                                 self._steps, grad_scale=1.0 / world)
@@ -163,16 +173,49 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
         for n in sizes:
             spans.append((off, off + n))
             off += (n + 63) // 64 * 64                     # keep every layer 256-byte aligned
-        flat = torch.zeros(off, device=dev, dtype=torch.float32)
-        st = {"param": flat, "grad": torch.zeros_like(flat), "exp_avg": torch.zeros_like(flat),
-              "exp_avg_sq": torch.zeros_like(flat), "spans": spans}
+        peer = self._alloc_peer_buffers(off, dev)          # N > 1: parameters / gradient in NVLink peer memory
+        flat = peer["param"] if peer else torch.zeros(off, device=dev, dtype=torch.float32)
+        grad = peer["grad"] if peer else torch.zeros_like(flat)
+        st = {"param": flat, "grad": grad, "exp_avg": torch.zeros_like(flat),
+              "exp_avg_sq": torch.zeros_like(flat), "spans": spans, "peer": peer}
         with torch.no_grad():
             for m, (a, b) in zip(mods, spans):
                 flat[a:b].copy_(m.data.detach().reshape(-1).to(torch.float32))
                 m.data.data = flat[a:b].view_as(m.data)
                 m.data.grad = st["grad"][a:b].view_as(m.data)
+        if peer:                                           # replicas start identical (DDP broadcasts rank 0's weights)
+            torch.distributed.broadcast(flat, 0)
+            peer["handles"][0].barrier()
         self._fused = st
         return st
+
+    @staticmethod
+    def _alloc_peer_buffers(numel: int, dev) -> Optional[dict]:
+        """Flat parameter / gradient / flag buffers that every rank of the node can address (symmetric memory over
+        NVLink), for the fused reduce-scatter + Adam + all-gather kernel (smb_dist_adam_step).  None: single process, a
+        non-NCCL backend, SMB_DIST_ADAM=0, or symmetric memory unavailable -> plain all_reduce + local Adam."""
+        import os
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return None
+        if os.environ.get("SMB_DIST_ADAM", "1") == "0" or dist.get_backend() != "nccl" or dist.get_world_size() > 16:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            bufs, handles = {}, []
+            for name, n, dt in (("param", numel, torch.float32), ("grad", numel, torch.float32),
+                                ("flags", 64, torch.int32)):
+                t = symm.empty(n, dtype=dt, device=dev)
+                handles.append(symm.rendezvous(t, dist.group.WORLD))
+                t.zero_()
+                bufs[name] = t
+            bufs["handles"] = handles
+            bufs["ptrs"] = {name: [int(p) for p in h.buffer_ptrs] for name, h in zip(("param", "grad", "flags"), handles)}
+            return bufs
+        except Exception as e:                             # pragma: no cover - depends on the box
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e!r}); falling back to NCCL all_reduce + local Adam")
+            return None
 
     def _layer_tensors(self) -> List[torch.Tensor]:
         return [m.data.detach() for m in self._layer_modules()]
