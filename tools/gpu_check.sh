@@ -21,5 +21,7 @@ run pipeline_simt tests/test_gpu_pipeline.py -k "simt"
 run pipeline_tc tests/test_gpu_pipeline.py -k "not simt"
 run fullsize tests/test_gpu_fullsize_properties.py
 run cli tests/test_gpu_cli.py
+run view tests/test_gpu_view_store.py
+run dist tests/test_gpu_dist_adam.py
 echo "=== smoke"
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log; tail -n 3 gpurun_out/smoke.log
