@@ -166,6 +166,14 @@ int smb_level_begin(smb_ctx* ctx, int H, int W);
 /* VGG forward of image (3,H,W) fp32 up to and including conv `last_conv` (0 = conv1_1 .. 12 = conv5_1). */
 int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv, void* stream);
 
+/* Inference-only forward (the content-target pass VGG(rgb), cs:294, and any other feature extraction that is never
+ * back-propagated): same arithmetic, but only the layers whose bit is set in keep_mask (bit i = conv index i) are
+ * guaranteed to be readable afterwards (smb_level_get_feature*, smb_level_gram).  A layer that only feeds a max-pool
+ * is pooled inside the conv epilogue and never written at full resolution.  Loss terms and smb_level_backward are
+ * rejected on the slot until the next smb_level_forward. */
+int smb_level_forward_features(smb_ctx* ctx, int slot, const float* image, int last_conv, unsigned int keep_mask,
+                               void* stream);
+
 /* Export relu(conv_i) as fp32 (C,h,w); query its shape. */
 int smb_level_feature_shape(smb_ctx* ctx, int slot, int conv, int* C, int* h, int* w);
 int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, void* stream);

@@ -53,6 +53,7 @@ PROTOTYPES = [
     ("smb_ctx_load_vgg", _i, [_p, _pp, _pp, _i]),
     ("smb_level_begin", _i, [_p, _i, _i]),
     ("smb_level_forward", _i, [_p, _i, _p, _i, _p]),
+    ("smb_level_forward_features", _i, [_p, _i, _p, _i, C.c_uint, _p]),
     ("smb_level_feature_shape", _i, [_p, _i, _i, _ip, _ip, _ip]),
     ("smb_level_get_feature", _i, [_p, _i, _i, _p, _p]),
     ("smb_level_get_feature_nhwc", _i, [_p, _i, _i, _p, _p]),

@@ -103,6 +103,8 @@ struct Slot {
   float* fmask[SMB_NUM_VGG_CONVS];
   bool fused[SMB_NUM_VGG_CONVS], fused_masked[SMB_NUM_VGG_CONVS];
   int last_done = -1;
+  unsigned valid = 0;            // bit i: y[i] holds the features of the last forward (inference-only passes skip some)
+  bool inference_only = false;   // last forward was smb_level_forward_features: no loss terms, no backward
   DeviceArena arena;
   Slot() {
     for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) {
@@ -594,13 +596,19 @@ int smb_level_begin(smb_ctx* ctx, int H, int W) {
   return (int)ctx->slots.size() - 1;
 }
 
-int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv, void* stream) {
+// keep_mask < 0: training forward (every layer materialised).  Otherwise an inference-only pass: a layer that only
+// feeds a max-pool and is not in keep_mask leaves igemm_ph through the pooled epilogue (a quarter of the bytes, no
+// pool launch) and its full-resolution features are never written.
+static int level_forward_impl(smb_ctx* ctx, int slot, const float* image, int last_conv, long long keep_mask,
+                              void* stream) {
   Slot* sp = get_slot(ctx, slot);
   if (!sp) return SMB_ERR_ARG;
   Slot& s = *sp;
   SMB_REQUIRE(ctx->vgg_loaded, "level_forward: VGG weights not loaded (smb_ctx_load_vgg)");
   SMB_REQUIRE(image && last_conv >= 0 && last_conv < SMB_NUM_VGG_CONVS, "level_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool inference = keep_mask >= 0;
+  s.valid = 0;
   {
     Epilogue ep;
     ep.relu = 1;
@@ -613,26 +621,45 @@ int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv,
     else
       rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
     if (rc) return rc;
+    s.valid |= 1u;
   }
+  bool pooled_ready = false;     // pooled[i] was written by the epilogue of conv i-1
   for (int i = 1; i <= last_conv; ++i) {
     Act x = s.y[i - 1];
     if (kPoolBefore[i]) {
-      ScopedTimer tm(ctx->timing, CLS_POOL, st);
-      int rc = launch_maxpool_fwd(s.y[i - 1], s.pooled[i], st);
-      if (rc) return rc;
+      if (!pooled_ready) {
+        ScopedTimer tm(ctx->timing, CLS_POOL, st);
+        int rc = launch_maxpool_fwd(s.y[i - 1], s.pooled[i], st);
+        if (rc) return rc;
+      }
       x = s.pooled[i];
     }
+    const bool pool_out = inference && ctx->conv_impl == IMPL_TC_PH && i < last_conv && kPoolBefore[i + 1] &&
+                          !((keep_mask >> i) & 1) && kCout[i] % 64 == 0;
     Epilogue ep;
     ep.bias = ctx->conv[i].bias;
     ep.relu = 1;
-    ep.out_hi = s.y[i].hi;
-    ep.out_lo = s.y[i].lo;
+    ep.out_hi = pool_out ? s.pooled[i + 1].hi : s.y[i].hi;
+    ep.out_lo = pool_out ? s.pooled[i + 1].lo : s.y[i].lo;
+    ep.pool2x2 = pool_out ? 1 : 0;
     int rc = igemm_timed(ctx, CLS_IGEMM_FWD, x, ctx->conv[i].fwd, ep, st);
     if (rc) return rc;
+    pooled_ready = pool_out;
+    if (!pool_out) s.valid |= 1u << i;
   }
   s.last_done = last_conv;
+  s.inference_only = inference;
   for (int i = 0; i < SMB_NUM_VGG_CONVS; ++i) s.has_pend[i] = s.fused[i] = false;
   return SMB_OK;
+}
+
+int smb_level_forward(smb_ctx* ctx, int slot, const float* image, int last_conv, void* stream) {
+  return level_forward_impl(ctx, slot, image, last_conv, -1, stream);
+}
+
+int smb_level_forward_features(smb_ctx* ctx, int slot, const float* image, int last_conv, unsigned int keep_mask,
+                               void* stream) {
+  return level_forward_impl(ctx, slot, image, last_conv, (long long)keep_mask, stream);
 }
 
 int smb_level_feature_shape(smb_ctx* ctx, int slot, int conv, int* C, int* h, int* w) {
@@ -650,6 +677,7 @@ int smb_level_get_feature(smb_ctx* ctx, int slot, int conv, float* out_nchw, voi
   if (!sp) return SMB_ERR_ARG;
   SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && out_nchw, "get_feature: conv %d not computed (last=%d)", conv,
               sp->last_done);
+  SMB_REQUIRE((sp->valid >> conv) & 1u, "get_feature: conv %d was not kept by smb_level_forward_features", conv);
   return launch_act_to_nchw(sp->y[conv], out_nchw, (cudaStream_t)stream);
 }
 
@@ -671,6 +699,7 @@ int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc
   if (!sp) return SMB_ERR_ARG;
   SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && out_nhwc, "get_feature_nhwc: conv %d not computed (last=%d)",
               conv, sp->last_done);
+  SMB_REQUIRE((sp->valid >> conv) & 1u, "get_feature_nhwc: conv %d was not kept by smb_level_forward_features", conv);
   const Act& a = sp->y[conv];
   if (a.elems() == 0) return SMB_OK;
   SMB_LAUNCH(smb::act_to_f32_kernel, (unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1, 256), 148 * 16), 256, 0, (cudaStream_t)stream, a, out_nhwc);
@@ -690,6 +719,7 @@ int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float
   if (!sp) return SMB_ERR_ARG;
   SMB_REQUIRE(conv >= 0 && conv <= sp->last_done && gram_out, "level_gram: conv %d not computed (last=%d)", conv,
               sp->last_done);
+  SMB_REQUIRE((sp->valid >> conv) & 1u, "level_gram: conv %d was not kept by smb_level_forward_features", conv);
   cudaStream_t st = (cudaStream_t)stream;
   int ns = 0;
   int rc = gram_partials(ctx, *sp, conv, rowmask, &ns, st);
@@ -706,6 +736,10 @@ int smb_level_style_term(smb_ctx* ctx, int slot, int conv, const float* rowmask,
   if (!sp) return SMB_ERR_ARG;
   Slot& s = *sp;
   SMB_REQUIRE(conv >= 0 && conv <= s.last_done, "style_term: conv %d not computed (last=%d)", conv, s.last_done);
+  if (s.inference_only) {
+    set_error("style_term: the slot holds an inference-only forward (smb_level_forward_features)");
+    return SMB_ERR_STATE;
+  }
   SMB_REQUIRE(target0 && loss_accum, "style_term: null target or loss accumulator");
   cudaStream_t st = (cudaStream_t)stream;
   const Act& feat = s.y[conv];
@@ -752,6 +786,10 @@ int smb_level_content_term(smb_ctx* ctx, int slot, int conv, const float* target
   if (!sp) return SMB_ERR_ARG;
   Slot& s = *sp;
   SMB_REQUIRE(conv >= 0 && conv <= s.last_done, "content_term: conv %d not computed (last=%d)", conv, s.last_done);
+  if (s.inference_only) {
+    set_error("content_term: the slot holds an inference-only forward (smb_level_forward_features)");
+    return SMB_ERR_STATE;
+  }
   SMB_REQUIRE(target_nhwc && rowmask && loss_accum, "content_term: null argument");
   int rc = ensure_pend(s, conv);
   if (rc) return rc;

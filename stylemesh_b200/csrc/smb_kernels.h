@@ -89,6 +89,7 @@ struct Epilogue {
   const float* addend = nullptr;          // [P][N] fp32
   const __nv_bfloat16* sign_hi = nullptr; // [P][N] (hi plane of the forward activation: ReLU backward mask)
   int relu = 0;
+  int pool2x2 = 0;                        // igemm_ph only: out_hi/out_lo are the (H/2, W/2) planes of maxpool2x2(v)
   __nv_bfloat16* out_hi = nullptr;
   __nv_bfloat16* out_lo = nullptr;
   float* out_f32 = nullptr;

@@ -70,7 +70,8 @@ struct IGemm5Params {
   int resident;               // 1: one K-chunk, one N tile -> the 9 B tiles are loaded once and stay in stages 0..8
   int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
-  int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do
+  int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do,
+                              // 3: only maxpool2x2 of the hi/lo planes is stored (inference-only forward into a pool)
   unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
   Epilogue ep;
 };
@@ -689,6 +690,40 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (valid) epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
         } else {
           epilogue_apply<32>(prm.ep, p, n0 + c, prm.N, v, valid);
+          if (prm.tma_out == 3) {
+            // MaxPool2d(2,2) in registers: pixel (py, px) of the 16 x 8 patch is lane (py % 4) * 8 + px of quarter
+            // py / 4, so the 2x2 window partners are lane ^ 1 and lane ^ 8.  Lanes with both bits clear hold the
+            // window maximum = pooled pixel (py / 2, px / 2) of the 8 x 4 pooled patch; windows that stick out of the
+            // image lie outside the pooled tensor (floor mode) and are clipped by the tensor store.
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+              v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+            }
+            if ((lane & 9) == 0) {
+              const uint32_t prow = (uint32_t)((q * 2 + (lane >> 4)) * 4 + ((lane & 7) >> 1));
+              const uint32_t pbase = s_out + prow * 128u, psw = prow & 7u, pch0 = (uint32_t)((c & 63) >> 3);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 h, l;
+                split2_pack(v[8 * j], v[8 * j + 1], h.x, l.x);
+                split2_pack(v[8 * j + 2], v[8 * j + 3], h.y, l.y);
+                split2_pack(v[8 * j + 4], v[8 * j + 5], h.z, l.z);
+                split2_pack(v[8 * j + 6], v[8 * j + 7], h.w, l.w);
+                const uint32_t a = pbase + (((pch0 + (uint32_t)j) ^ psw) << 4);
+                i5_sts128(a, h);
+                i5_sts128(a + I5_OUT_PLANE, l);
+              }
+            }
+            fence_proxy_async_smem();
+            i5_epi_bar();
+            if (epi_leader) {
+              i5_tma_store_3d(&tmO_hi, sOut, n0 + (c & ~63), x0 >> 1, y0 >> 1);
+              i5_tma_store_3d(&tmO_lo, sOut + I5_OUT_PLANE, n0 + (c & ~63), x0 >> 1, y0 >> 1);
+              i5_bulk_commit();
+            }
+            continue;
+          }
           // pixel `row` of the patch is 128-byte row `row` of the staging tile; 16-byte chunk index XOR (row & 7)
           // = the SWIZZLE_128B pattern the tensor store expects (conflict free: 8 lanes cover 8 distinct chunks)
           const uint32_t rbase = s_out + (uint32_t)row * 128u;
@@ -839,15 +874,16 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   // keeps the per-thread stores
   prm.tma_out = 0;
   if (BN >= 64 && !ep.outm_hi && !ep.out_planar3) {
-    if (ep.out_hi && ep.out_lo && !ep.out_f32) prm.tma_out = 1;
+    if (ep.out_hi && ep.out_lo && !ep.out_f32) prm.tma_out = ep.pool2x2 ? 3 : 1;
     else if (ep.out_f32 && !ep.out_hi) prm.tma_out = 2;
   }
+  SMB_REQUIRE(!ep.pool2x2 || prm.tma_out == 3, "igemm_ph: the pooled epilogue needs hi/lo outputs only and N %% 64 == 0");
   static int no_tma_out = -1;
   if (no_tma_out < 0) {
     const char* e = getenv("SMB_PH_DIRECT_STORES");     // experiment knob: 1 = per-thread global stores as in igemm_tc2
     no_tma_out = (e && atoi(e)) ? 1 : 0;
   }
-  if (no_tma_out) prm.tma_out = 0;
+  if (no_tma_out && prm.tma_out != 3) prm.tma_out = 0;
   prm.resident = (prm.kchunks == 1 && prm.tiles_n == 1 && Cfg::NB >= 9) ? 1 : 0;
   {
     static int no_resident = -1;
@@ -884,7 +920,15 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     rc = make_tmap_bf16(&tmB_lo, b.lo, 3, dims, strides, box);
     if (rc) return rc;
   }
-  if (prm.tma_out == 1) {
+  if (prm.tma_out == 3) {
+    const uint64_t dims[3] = {(uint64_t)b.N, (uint64_t)(a.W / 2), (uint64_t)(a.H / 2)};       // MaxPool2d floor mode
+    const uint64_t strides[2] = {(uint64_t)b.N * 2, (uint64_t)(a.W / 2) * b.N * 2};
+    const uint32_t box[3] = {64u, (uint32_t)(I5_TW / 2), (uint32_t)(I5_TH / 2)};
+    rc = make_tmap_bf16(&tmO_hi, ep.out_hi, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmO_lo, ep.out_lo, 3, dims, strides, box);
+    if (rc) return rc;
+  } else if (prm.tma_out == 1) {
     const uint64_t dims[3] = {(uint64_t)b.N, (uint64_t)a.W, (uint64_t)a.H};
     const uint64_t strides[2] = {(uint64_t)b.N * 2, (uint64_t)a.W * b.N * 2};
     const uint32_t box[3] = {64u, (uint32_t)I5_TW, (uint32_t)I5_TH};

@@ -358,10 +358,19 @@ class VGGEngine:
                 for i, name in enumerate(self.TIMING_CLASSES)}
 
     # -- forward / features ---------------------------------------------------------------------------------
-    def forward(self, slot: int, image: torch.Tensor, last_conv: int) -> None:
+    def forward(self, slot: int, image: torch.Tensor, last_conv: int, keep=None) -> None:
+        """keep=None: training forward.  keep=[conv indices]: inference-only pass that guarantees only those layers'
+        features (layers that merely feed a pool are pooled in the conv epilogue and never materialised)."""
         image = _require_cuda_f32(image, "image")
-        _abi.check(self._lib.smb_level_forward(self._ctx, slot, _abi.ptr(image), int(last_conv),
-                                               _abi.current_stream()), "smb_level_forward")
+        if keep is None:
+            _abi.check(self._lib.smb_level_forward(self._ctx, slot, _abi.ptr(image), int(last_conv),
+                                                   _abi.current_stream()), "smb_level_forward")
+            return
+        mask = 0
+        for c in keep:
+            mask |= 1 << int(c)
+        _abi.check(self._lib.smb_level_forward_features(self._ctx, slot, _abi.ptr(image), int(last_conv), mask,
+                                                        _abi.current_stream()), "smb_level_forward_features")
 
     def feature_shape(self, slot: int, conv: int):
         c, h, w = C.c_int(), C.c_int(), C.c_int()

@@ -213,7 +213,7 @@ class ContentAndStyleLoss(nn.Module):
                 continue
             img = p[0].to(eng.device, torch.float32).contiguous()
             slot = eng.begin(img.shape[1], img.shape[2])
-            eng.forward(slot, img, max(convs))
+            eng.forward(slot, img, max(convs), keep=convs)      # style targets: Grams of these layers only
             per_entry[key] = []
             for c in convs:
                 _, h, w = eng.feature_shape(slot, c)
@@ -234,7 +234,7 @@ class ContentAndStyleLoss(nn.Module):
             img = target_content[0].contiguous()
             convs = [_eng.layer_index(n) for n in self.content_layers]
             slot = eng.begin(img.shape[1], img.shape[2])
-            eng.forward(slot, img, max(convs))
+            eng.forward(slot, img, max(convs), keep=convs)      # never back-propagated: inference-only pass
             for name, c in zip(self.content_layers, convs):
                 C_, hc, wc = eng.feature_shape(slot, c)
                 nhwc = None

@@ -138,7 +138,7 @@ class VGGEngine:
     def release_slots(self):
         self.slots = []
 
-    def forward(self, slot, image, last_conv):
+    def forward(self, slot, image, last_conv, keep=None):
         s = self.slots[slot]
         with torch.enable_grad():            # the product may call us from inside an autograd.Function (no-grad mode)
             img = image.detach().clone().requires_grad_(True)

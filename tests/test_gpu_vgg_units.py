@@ -128,3 +128,31 @@ def test_first_layer_tcgen05_ragged_sizes(h, w, tmp_path):
     want = F.relu(F.conv2d(x, sd["conv1_1.weight"], sd["conv1_1.bias"], padding=1))
     assert got.shape == want.shape
     assert _rel(got, want) < 2e-5, _rel(got, want)
+
+
+@pytest.mark.parametrize("h,w", [(64, 96), (37, 53), (48, 200), (33, 64)])
+def test_inference_only_forward_pools_in_the_conv_epilogue(h, w, tmp_path):
+    """smb_level_forward_features (the content-target pass, cs:294): layers that only feed a pool leave igemm_ph through
+    the 2x2-max epilogue.  Max-pooling selects one of four values, so the kept features are value-identical to the
+    training forward's (odd sizes: MaxPool2d floor mode drops the trailing row / column)."""
+    from stylemesh_b200 import engine as E, synthetic as syn
+    sd = syn.make_vgg_state_dict(5, bias_scale=0.3)
+    eng = E.VGGEngine(sd)
+    g = torch.Generator().manual_seed(h + w)
+    img = (torch.rand(3, h, w, generator=g) * 255 - 110).cuda()
+    slot = eng.begin(h, w)
+    eng.forward(slot, img, 9)
+    want = {c: eng.feature(slot, c).clone() for c in (2, 4, 8, 9)}
+    eng.forward(slot, img, 9, keep=[9])
+    assert torch.equal(eng.feature(slot, 9), want[9])
+    from stylemesh_b200._abi import StyleMeshB200Error
+    with pytest.raises(StyleMeshB200Error, match="not kept"):
+        eng.feature(slot, 3)                      # conv2_2 only fed pool2: never materialised
+    eng.forward(slot, img, 9, keep=[2, 4, 8, 9])  # conv2_1 / conv3_1 / conv4_1 follow the pools: always materialised
+    for c in (2, 4, 8, 9):
+        assert torch.equal(eng.feature(slot, c), want[c]), c
+    eng.forward(slot, img, 9, keep=[1, 3, 7, 9])  # keeping the pool feeders falls back to the separate pool kernel
+    assert torch.equal(eng.feature(slot, 9), want[9])
+    eng.forward(slot, img, 9)                     # a training forward afterwards sees nothing stale
+    for c in (2, 4, 8, 9):
+        assert torch.equal(eng.feature(slot, c), want[c]), c
