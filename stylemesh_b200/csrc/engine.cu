@@ -223,8 +223,10 @@ static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, c
     return SMB_ERR_STATE;
   }
   if (impl == IMPL_TC_PH)
-    return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st, ft) : launch_igemm_tc2(a, b, ep, st);
-  if (impl == IMPL_TC_HALO) return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_halo(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
+    return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st, ft)
+                                                         : launch_igemm_tc2(a, b, ep, st);
+  if (impl == IMPL_TC_HALO)
+    return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_halo(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_PAIR) return (b.N % 128 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
@@ -702,7 +704,8 @@ int smb_level_get_feature_nhwc(smb_ctx* ctx, int slot, int conv, float* out_nhwc
   SMB_REQUIRE((sp->valid >> conv) & 1u, "get_feature_nhwc: conv %d was not kept by smb_level_forward_features", conv);
   const Act& a = sp->y[conv];
   if (a.elems() == 0) return SMB_OK;
-  SMB_LAUNCH(smb::act_to_f32_kernel, (unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1, 256), 148 * 16), 256, 0, (cudaStream_t)stream, a, out_nhwc);
+  SMB_LAUNCH(smb::act_to_f32_kernel, (unsigned)std::min<int64_t>(ceil_div64(a.elems() >> 1,
+             256), 148 * 16), 256, 0, (cudaStream_t)stream, a, out_nhwc);
   return SMB_OK;
 }
 
@@ -725,7 +728,8 @@ int smb_level_gram(smb_ctx* ctx, int slot, int conv, const float* rowmask, float
   int rc = gram_partials(ctx, *sp, conv, rowmask, &ns, st);
   if (rc) return rc;
   const int64_t CC = (int64_t)sp->y[conv].C * sp->y[conv].C;
-  SMB_LAUNCH(gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st, sp->gram_partial, ns, CC, inv_n, gram_out);
+  SMB_LAUNCH(gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st,
+             sp->gram_partial, ns, CC, inv_n, gram_out);
   return SMB_OK;
 }
 
@@ -1089,7 +1093,8 @@ int smb_unit_gram(int impl, const float* f, int C, int H, int W, const float* ro
   rc = gram(impl, a, rowmask, m, partial, ns, st);
   if (rc) return rc;
   const int64_t CC = (int64_t)C * C;
-  SMB_LAUNCH(smb::gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st, partial, ns, CC, inv_n, G);
+  SMB_LAUNCH(smb::gram_reduce_kernel, (unsigned)std::min<int64_t>(ceil_div64(CC, 256), 592), 256, 0, st, partial, ns,
+             CC, inv_n, G);
   SMB_CUDA_CHECK(cudaStreamSynchronize(st));
   return SMB_OK;
 }

@@ -36,6 +36,10 @@ struct ConvFirstParams {
   Epilogue ep;
 };
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // byte offset of 16-byte chunk `j` of row `r` inside a 1024-byte-aligned SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
@@ -202,8 +206,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __grid_co
           split2_pack(v[8 * j + 4], v[8 * j + 5], h.z, l.z);
           split2_pack(v[8 * j + 6], v[8 * j + 7], h.w, l.w);
           const uint32_t a = rbase + ((((uint32_t)(c >> 3) + (uint32_t)j) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + CF_OUT_BYTES), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w) : "memory");
+          sts128(a, h);
+          sts128(a + CF_OUT_BYTES, l);
         }
       }
       if (prm.tma_out) {                   // one tensor store per plane; pixels outside the image are clipped by TMA

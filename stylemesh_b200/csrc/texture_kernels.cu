@@ -393,13 +393,15 @@ int launch_uv_sample_fwd(const TexLayerSet& tex, const float* grid, int H, int W
                          float* out, cudaStream_t st) {
   const int npix = H * W;
   if (npix == 0) return SMB_OK;
-  SMB_LAUNCH(uv_sample_fwd_kernel, ceil_div(npix, 256), 256, 0, st, tex, reinterpret_cast<const float2*>(grid), npix, clamp_lo, clamp_hi, out);
+  SMB_LAUNCH(uv_sample_fwd_kernel, ceil_div(npix, 256), 256, 0, st, tex, reinterpret_cast<const float2*>(grid), npix,
+             clamp_lo, clamp_hi, out);
   return SMB_OK;
 }
 
 int launch_uv_texel_index(const float* grid, int npix, int W, int H, int* xy0, float* w4, cudaStream_t st) {
   if (npix == 0) return SMB_OK;
-  SMB_LAUNCH(uv_texel_index_kernel, ceil_div(npix, 256), 256, 0, st, reinterpret_cast<const float2*>(grid), npix, W, H, xy0, w4);
+  SMB_LAUNCH(uv_texel_index_kernel, ceil_div(npix, 256), 256, 0, st, reinterpret_cast<const float2*>(grid), npix, W, H,
+             xy0, w4);
   return SMB_OK;
 }
 
@@ -407,7 +409,8 @@ int launch_uv_scatter_bwd(const TexLayerSet& gtex, const float* grid, int H, int
                           const float* hook0, const float* hook1, cudaStream_t st) {
   const int npix = H * W;
   if (npix == 0) return SMB_OK;
-  SMB_LAUNCH(uv_scatter_bwd_kernel, ceil_div(npix, 256), 256, 0, st, gtex, reinterpret_cast<const float2*>(grid), npix, gout, hook0, hook1);
+  SMB_LAUNCH(uv_scatter_bwd_kernel, ceil_div(npix, 256), 256, 0, st, gtex, reinterpret_cast<const float2*>(grid), npix,
+             gout, hook0, hook1);
   return SMB_OK;
 }
 

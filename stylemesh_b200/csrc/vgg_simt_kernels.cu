@@ -730,7 +730,8 @@ int launch_gram_mse(const float* partial, int nsplit, int C, float inv_n, const 
 int launch_content_mse(const Act& f, const float* target_nhwc, const float* rowmask, float coef_loss,
                        float coef_grad, float* addend, float* loss_out, cudaStream_t st) {
   if (f.elems() == 0) return SMB_OK;
-  SMB_LAUNCH(content_mse_kernel, grid_for(f.elems() >> 3, 256, 148 * 8), 256, 0, st, f, target_nhwc, rowmask, coef_loss, coef_grad, addend, loss_out);
+  SMB_LAUNCH(content_mse_kernel,
+             grid_for(f.elems() >> 3, 256, 148 * 8), 256, 0, st, f, target_nhwc, rowmask, coef_loss, coef_grad, addend, loss_out);
   return SMB_OK;
 }
 

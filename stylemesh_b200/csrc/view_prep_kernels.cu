@@ -84,14 +84,16 @@ __global__ void __launch_bounds__(256) view_resize_linear_kernel(const TIn* __re
     if (WORK_F32) {
       const float ax = (float)t.xa[x], ay = (float)t.ya[y];
       const float bx = __fsub_rn(1.f, ax), by = __fsub_rn(1.f, ay);
-      const float r0 = __fadd_rn(__fmul_rn((float)src[(int64_t)y0 * Ws + x0], bx), __fmul_rn((float)src[(int64_t)y0 * Ws + x1], ax));
-      const float r1 = __fadd_rn(__fmul_rn((float)src[(int64_t)y1 * Ws + x0], bx), __fmul_rn((float)src[(int64_t)y1 * Ws + x1], ax));
+      const int64_t o0 = (int64_t)y0 * Ws, o1 = (int64_t)y1 * Ws;
+      const float r0 = __fadd_rn(__fmul_rn((float)src[o0 + x0], bx), __fmul_rn((float)src[o0 + x1], ax));
+      const float r1 = __fadd_rn(__fmul_rn((float)src[o1 + x0], bx), __fmul_rn((float)src[o1 + x1], ax));
       dst[p] = (double)__fadd_rn(__fmul_rn(r0, by), __fmul_rn(r1, ay));
     } else {
       const double ax = t.xa[x], ay = t.ya[y];
       const double bx = __dsub_rn(1.0, ax), by = __dsub_rn(1.0, ay);
-      const double s00 = load_depth<TIn>(src, (int64_t)y0 * Ws + x0, divisor), s01 = load_depth<TIn>(src, (int64_t)y0 * Ws + x1, divisor);
-      const double s10 = load_depth<TIn>(src, (int64_t)y1 * Ws + x0, divisor), s11 = load_depth<TIn>(src, (int64_t)y1 * Ws + x1, divisor);
+      const int64_t o0 = (int64_t)y0 * Ws, o1 = (int64_t)y1 * Ws;
+      const double s00 = load_depth<TIn>(src, o0 + x0, divisor), s01 = load_depth<TIn>(src, o0 + x1, divisor);
+      const double s10 = load_depth<TIn>(src, o1 + x0, divisor), s11 = load_depth<TIn>(src, o1 + x1, divisor);
       const double r0 = __dadd_rn(__dmul_rn(s00, bx), __dmul_rn(s01, ax));
       const double r1 = __dadd_rn(__dmul_rn(s10, bx), __dmul_rn(s11, ax));
       dst[p] = __dadd_rn(__dmul_rn(r0, by), __dmul_rn(r1, ay));
@@ -233,15 +235,19 @@ int launch_view_resize_linear(const void* src, int src_type, double divisor, int
   switch (src_type) {
     case 0:
       if (same) SMB_LAUNCH(view_to_f64_kernel<double>, blocks_for(n), 256, 0, st, (const double*)src, divisor, n, dst);
-      else SMB_LAUNCH((view_resize_linear_kernel<double, false>), blocks_for(n), 256, 0, st, (const double*)src, divisor, Hs, Ws, t, Hd, Wd, dst);
+      else SMB_LAUNCH((view_resize_linear_kernel<double, false>), blocks_for(n), 256, 0, st, (const double*)src,
+          divisor, Hs, Ws, t, Hd, Wd, dst);
       break;
     case 1:
       if (same) SMB_LAUNCH(view_to_f64_kernel<float>, blocks_for(n), 256, 0, st, (const float*)src, divisor, n, dst);
-      else SMB_LAUNCH((view_resize_linear_kernel<float, true>), blocks_for(n), 256, 0, st, (const float*)src, divisor, Hs, Ws, t, Hd, Wd, dst);
+      else SMB_LAUNCH((view_resize_linear_kernel<float, true>), blocks_for(n), 256, 0, st, (const float*)src, divisor,
+          Hs, Ws, t, Hd, Wd, dst);
       break;
     case 2:
-      if (same) SMB_LAUNCH(view_to_f64_kernel<unsigned short>, blocks_for(n), 256, 0, st, (const unsigned short*)src, divisor, n, dst);
-      else SMB_LAUNCH((view_resize_linear_kernel<unsigned short, false>), blocks_for(n), 256, 0, st, (const unsigned short*)src, divisor, Hs, Ws, t, Hd, Wd, dst);
+      if (same) SMB_LAUNCH(view_to_f64_kernel<unsigned short>, blocks_for(n), 256, 0, st, (const unsigned short*)src,
+          divisor, n, dst);
+      else SMB_LAUNCH((view_resize_linear_kernel<unsigned short, false>), blocks_for(n), 256, 0, st,
+          (const unsigned short*)src, divisor, Hs, Ws, t, Hd, Wd, dst);
       break;
     default:
       set_error("view_resize_linear: src_type %d (0 = float64, 1 = float32, 2 = uint16 / divisor)", src_type);
