@@ -2,11 +2,11 @@
 scripts/train/optimize_texture_*.sh presets run unchanged on the B200 path.
 
 In scope: flag parsing, model construction, the training loop (lightning_shim.Trainer), texture export, and
-`--dataset scannet`: one scene in the reference's directory layout, prepared once on the device and kept resident
-(stylemesh_b200/data).  `--dataset synthetic` generates seeded views in memory.
-Out of scope (SURVEY §2 #6,#9-#11): the Matterport house/region loader (register a DataModule factory with
-`register_datamodule`; its pixel work is covered by ViewStore(mask_uses_depth=False, depth_divisor=4000)) and the
-post-run OpenGL mip-map render / video / LPIPS evaluation.
+`--dataset scannet|matterport`: one scene / house region in the reference's directory layout, prepared once on the
+device and kept resident (stylemesh_b200/data, SURVEY §8f.2).  `--dataset synthetic` generates seeded views in memory;
+other datasets plug in through `register_datamodule`.
+Out of scope (SURVEY §2 #6,#9-#11): the multi-scene dataset classes and the post-run OpenGL mip-map render / video /
+LPIPS evaluation.
 """
 from __future__ import annotations
 
@@ -89,6 +89,9 @@ def main(args):
     elif args.dataset == "scannet":                    # optimize.py:44-63 on the GPU-resident view store
         from ..data.scannet_scene import ScanNetViewStoreDataModule
         dm = ScanNetViewStoreDataModule(args)
+    elif args.dataset == "matterport":                 # optimize.py:65-88
+        from ..data.matterport_scene import MatterportViewStoreDataModule
+        dm = MatterportViewStoreDataModule(args)
     else:
         raise ValueError(f"Unsupported dataset: {args.dataset} (file loaders are outside the B200 hot path; register "
                          f"one with stylemesh_b200.model.optimize.register_datamodule or use --dataset synthetic)")

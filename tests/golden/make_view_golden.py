@@ -70,6 +70,54 @@ def write_scene(root):
     return os.path.join(root, "train", "images"), raw
 
 
+MP_HOUSE = "house0"
+MP_NAMES = ["0e92a69a50414253_i0_0", "0e92a69a50414253_i1_2", "5b9b2794954e4694_i0_1"]   # sort: hash, camera*100 + yaw
+
+
+def write_matterport(root):
+    """One region of one house in the Matterport layout (data/matterport_dataset.py:96-255); reuses the ScanNet
+    scene's pixel content with the Matterport file names, 1/4000 m depth units and an `.intrinsics.txt` file."""
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    rp = os.path.join(root, "v1", "scans", MP_HOUSE, "rendered", "region_0")
+    sizes = {24: 32, 32: 43, 48: 64, 64: 85}
+    for d in ["color", "depth", "pose", "angle"] + [f"uv_{w}_{h}" for h, w in sizes.items()]:
+        os.makedirs(os.path.join(rp, d))
+    raw = {}
+    order = [2, 0, 1]                                  # files are written out of order: the reader has to sort them
+    for i in order:
+        name = MP_NAMES[i]
+        H, W = COLOR_HW
+        rgb = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        Image.fromarray(rgb).save(os.path.join(rp, "color", name + ".png"))
+        yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+        depth_m = 0.2 + 2.2 * ((0.7 * xx / W + yy / H + 0.21 * i) % 1.0)
+        depth_q = np.round(depth_m * 4000).astype(np.uint16)
+        depth_q[(3 * xx + yy + 5 * i) % 19 == 0] = 0
+        Image.fromarray(depth_q).save(os.path.join(rp, "depth", name.replace("_i", "_d") + ".png"))
+        pose = np.eye(4, dtype=np.float64)
+        pose[:3, 3] = rng.normal(size=3)
+        np.savetxt(os.path.join(rp, "pose", name + ".png.pose.txt"), pose, delimiter=" ")
+        raw[f"mp_rgb_{i}"], raw[f"mp_depth_q_{i}"], raw[f"mp_pose_{i}"] = rgb, depth_q, pose.astype(np.float32)
+        for h, w in sizes.items():
+            y2, x2 = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            u = (0.05 + 0.9 * x2 / w + 0.02 * np.cos(y2 / 4.0 + i)).astype(np.float32)
+            v = (0.1 + 0.8 * y2 / h + 0.03 * np.sin(x2 / 6.0 - i)).astype(np.float32)
+            uv = np.stack([u, v, np.full_like(u, 0.5)], axis=2)
+            uv[((x2 * 4 // w + y2 * 3 // h + i) % 5 == 0) & (y2 > h // 4)] = 0.0
+            np.save(os.path.join(rp, f"uv_{w}_{h}", name + ".png.uvs.npy"), uv)
+            raw[f"mp_uv{h}_{i}"] = uv
+        ha, wa = 40, 54
+        y3, x3 = np.meshgrid(np.arange(ha), np.arange(wa), indexing="ij")
+        cosang = (0.1 + 0.9 * np.abs(np.sin(x3 / 8.0 - y3 / 11.0 + i))).astype(np.float32)
+        ang = np.stack([cosang, cosang * 0, cosang * 0], axis=2)
+        np.save(os.path.join(rp, "angle", name + ".png.angle.npy"), ang)
+        raw[f"mp_angle_{i}"] = ang
+    with open(os.path.join(rp, "pose", MP_NAMES[0] + ".png.intrinsics.txt"), "w") as f:
+        f.write("70.5 0 39.5\n0 71.25 29.5\n0 0 1\n80 60\n")
+    return os.path.join(root, "v1", "scans"), raw
+
+
 def import_reference():
     if not hasattr(np, "int"):
         np.int = int                                       # scannet_dataset.py:365
@@ -86,16 +134,18 @@ def import_reference():
     sys.modules["pytorch_lightning"] = pl
     sys.path.insert(0, REF)
     from data.scannet_single_scene_dataset import ScanNet_Single_House_Dataset
+    from data.matterport_single_scene_dataset import Matterport_Single_House_Dataset
     from model.texture.utils import get_rgb_transform, get_label_transform, get_uv_transform
     from model.losses.rgb_transform import pre
     from torchvision.transforms import Compose
-    return ScanNet_Single_House_Dataset, Compose([get_rgb_transform(), pre()]), get_label_transform(), get_uv_transform()
+    return (ScanNet_Single_House_Dataset, Matterport_Single_House_Dataset, Compose([get_rgb_transform(), pre()]),
+            get_label_transform(), get_uv_transform())
 
 
 def main():
     tmp = tempfile.mkdtemp(prefix="smb_view_golden_")
     root, raw = write_scene(tmp)
-    DS, t_rgb, t_label, t_uv = import_reference()
+    DS, MPDS, t_rgb, t_label, t_uv = import_reference()
     ds = DS(root_path=root, scene=SCENE, min_images=1, max_images=-1, transform_rgb=t_rgb, transform_label=t_label,
             transform_uv=t_uv, resize_size=RESIZE, pyramid_levels=3, min_pyramid_depth=MIN_DEPTH,
             min_pyramid_height=32, verbose=False)
@@ -117,6 +167,30 @@ def main():
                 out[f"ref_{n}_{i}"] = np.asarray(t)
     out["meta"] = np.asarray([N_VIEWS, RESIZE, len(ds.levels)], dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "view_prep.npz"), **out)
+
+    # Matterport: same pipeline, other file layout, depth / 4000, mask without the depth factor
+    mp_root, mp_raw = write_matterport(tmp)
+    mp = MPDS(root_path=mp_root, scene=MP_HOUSE, min_images=1, max_images=-1, transform_rgb=t_rgb,
+              transform_label=t_label, transform_uv=t_uv, resize_size=RESIZE, pyramid_levels=3,
+              min_pyramid_depth=MIN_DEPTH, min_pyramid_height=32, region_index=0, verbose=False)
+    mo = dict(mp_raw)
+    mo["levels"] = np.asarray(mp.levels, dtype=np.float64)
+    mo["all_levels"] = np.asarray(mp.all_levels, dtype=np.float64)
+    mo["names"] = np.asarray(MP_NAMES)
+    for i in range(len(mp)):
+        item = mp[i]
+        for n, t in zip(names, item):
+            if n == "uv":
+                for l, u in enumerate(t):
+                    mo[f"ref_uv{l}_{i}"] = np.asarray(u)
+            elif n == "idx":
+                mo[f"ref_idx_{i}"] = np.asarray(t)
+            else:
+                mo[f"ref_{n}_{i}"] = np.asarray(t)
+    mo["meta"] = np.asarray([len(mp), RESIZE, len(mp.levels)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "view_prep_matterport.npz"), **mo)
+    print("matterport levels", mo["levels"], "views", len(mp), "bytes",
+          os.path.getsize(os.path.join(HERE, "view_prep_matterport.npz")))
     for k in sorted(out):
         if k.startswith("ref_") and k.endswith("_0"):
             print(k, out[k].dtype, out[k].shape)

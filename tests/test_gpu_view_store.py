@@ -28,6 +28,17 @@ def test_store_matches_reference_tuples(gold, tmp_path):
         vsu.check_view_against_golden(v, gold, i)
 
 
+def test_matterport_store_matches_reference_tuples(tmp_path):
+    from stylemesh_b200.data.matterport_scene import MatterportRegion
+    from stylemesh_b200.data.scene_base import load_scene_into_store
+    mg = np.load(vsu.MP_GOLD)
+    root = vsu.write_matterport(mg, tmp_path)
+    reg = MatterportRegion(f"{root}/v1/scans/{vsu.MP_HOUSE}", region_index=0, pyramid_levels=3, min_pyramid_height=32)
+    store = load_scene_into_store(reg, "cuda", 30, min_pyramid_depth=1.0)
+    for i in range(3):
+        vsu.check_view_against_golden(store[i], mg, i)
+
+
 def test_kernels_equal_the_oracle_on_ragged_sizes():
     """Each kernel against the pinned numpy oracle on sizes that are not multiples of anything; integer outputs,
     gathers and the explicitly rounded float arithmetic must be bit-identical."""

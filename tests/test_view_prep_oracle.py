@@ -89,3 +89,23 @@ def test_intrinsics_rescale(gold):
     k[0, 0], k[1, 1], k[0, 2], k[1, 2] = 70.5, 71.25, 39.5, 29.5
     got = vo.modify_intrinsics(k, (80, 60), (40, 30))
     assert np.array_equal(got, gold["ref_intrinsics_0"])
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_matterport_variant(i):
+    """Depth in 1/4000 m (matterport_dataset.py:288) and a validity mask that ignores the depth (:304-307), against the
+    reference's Matterport_Single_House_Dataset on a synthetic house region."""
+    from PIL import Image
+    g = np.load(os.path.join(os.path.dirname(GOLD), "view_prep_matterport.npz"))
+    rgb = g[f"mp_rgb_{i}"]
+    size_wh = vo.resolve_resize(int(g["meta"][1]), (rgb.shape[1], rgb.shape[0]))
+    rgb_r = np.asarray(Image.fromarray(rgb).resize(size_wh))
+    uv = [g[f"mp_uv{int(h)}_{i}"] for h in g["levels"]]
+    out = vo.preprocess_view(rgb_r, uv, g[f"mp_angle_{i}"], np.asarray(g[f"mp_depth_q_{i}"]) / 4000.0, g["levels"], 1.0,
+                             size_wh, mask_uses_depth=False)
+    assert np.array_equal(out["mask"], g[f"ref_mask_{i}"])
+    assert np.array_equal(out["rounded_depth_level"], g[f"ref_rounded_depth_level_{i}"])
+    assert np.array_equal(out["other_depth_level"], g[f"ref_other_depth_level_{i}"])
+    assert np.array_equal(out["rgb"], g[f"ref_rgb_{i}"]) and np.array_equal(out["uv"][2], g[f"ref_uv2_{i}"])
+    assert np.allclose(out["depth"], g[f"ref_depth_{i}"], rtol=1e-6, atol=0)
+    assert np.allclose(out["interp_weight"], g[f"ref_interp_weight_{i}"], rtol=0, atol=2e-6)

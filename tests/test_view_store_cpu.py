@@ -73,3 +73,20 @@ def test_datamodule_split_and_sampler(gold, tmp_path, monkeypatch):
     assert dm.train_indices == [0, 1] and dm.val_indices == [2]
     assert [int(b[8][0]) for b in dm.train_dataloader()] == [0, 0, 1, 1]
     assert [int(b[8][0]) for b in dm.val_dataloader()] == [2]
+
+
+def test_matterport_region_matches_the_reference(tmp_path, monkeypatch):
+    """Matterport layout (house / rendered / region_k, hash_iC_Y file names, depth in 1/4000 m, mask without the depth
+    factor) against the 13-tuples of the reference's Matterport_Single_House_Dataset."""
+    fake_engine.install(monkeypatch)
+    from stylemesh_b200.data.matterport_scene import MatterportRegion
+    from stylemesh_b200.data.scene_base import load_scene_into_store
+    gold = np.load(vsu.MP_GOLD)
+    root = vsu.write_matterport(gold, tmp_path)
+    reg = MatterportRegion(f"{root}/v1/scans/{vsu.MP_HOUSE}", region_index=0, pyramid_levels=3, min_pyramid_height=32)
+    assert len(reg) == 3 and not reg.rendered_depth and not reg.mask_uses_depth and reg.depth_divisor == 4000.0
+    assert reg.levels == gold["levels"].tolist() and reg.all_levels == gold["all_levels"].tolist()
+    assert [p.split("/")[-1].split(".")[0] for p in reg.colors] == [str(n) for n in gold["names"]]
+    store = load_scene_into_store(reg, "cpu", 30, min_pyramid_depth=1.0)
+    for i in range(3):
+        vsu.check_view_against_golden(store[i], gold, i)

@@ -27,6 +27,32 @@ def write_scene(gold, root) -> str:
     return str(root)
 
 
+MP_HOUSE = "house0"
+MP_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "view_prep_matterport.npz")
+
+
+def write_matterport(gold, root) -> str:
+    """The Matterport-layout house of make_view_golden.py from the raw arrays in view_prep_matterport.npz."""
+    from PIL import Image
+    rp = os.path.join(str(root), "v1", "scans", MP_HOUSE, "rendered", "region_0")
+    names = [str(n) for n in gold["names"]]
+    heights = sorted({int(k[5:].split("_")[0]) for k in gold.files if k.startswith("mp_uv")})
+    widths = {h: gold[f"mp_uv{h}_0"].shape[1] for h in heights}
+    for d in ["color", "depth", "pose", "angle"] + [f"uv_{widths[h]}_{h}" for h in heights]:
+        os.makedirs(os.path.join(rp, d), exist_ok=True)
+    for i in (1, 2, 0):                                  # directory order must not matter
+        name = names[i]
+        Image.fromarray(gold[f"mp_rgb_{i}"]).save(os.path.join(rp, "color", name + ".png"))
+        Image.fromarray(gold[f"mp_depth_q_{i}"]).save(os.path.join(rp, "depth", name.replace("_i", "_d") + ".png"))
+        np.savetxt(os.path.join(rp, "pose", name + ".png.pose.txt"), gold[f"mp_pose_{i}"].astype(np.float64), delimiter=" ")
+        for h in heights:
+            np.save(os.path.join(rp, f"uv_{widths[h]}_{h}", name + ".png.uvs.npy"), gold[f"mp_uv{h}_{i}"])
+        np.save(os.path.join(rp, "angle", name + ".png.angle.npy"), gold[f"mp_angle_{i}"])
+    with open(os.path.join(rp, "pose", names[0] + ".png.intrinsics.txt"), "w") as f:
+        f.write("70.5 0 39.5\n0 71.25 29.5\n0 0 1\n80 60\n")
+    return str(root)
+
+
 NAMES = ["rgb", "extrinsics", "intrinsics", "depth", "depth_level", "rounded_depth_level", "other_depth_level",
          "interp_weight", "idx", "uv", "mask", "angle_guidance", "angle_degrees"]
 
