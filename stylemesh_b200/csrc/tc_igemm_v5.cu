@@ -49,7 +49,10 @@ struct I5Cfg {
   static constexpr int B_PLANE = (BN / 2) * 128;                 // this CTA's half of the B tile of one tap
   static constexpr int B_STAGE = 2 * B_PLANE;                    // hi + lo
   static constexpr int NB_FIT = (I5_SMEM_LIMIT - 1024 - 2 * I5_A_BUF - I5_OUT_BYTES - I5_BAR_BYTES) / B_STAGE;
-  static constexpr int TMEM_NEED = 2 * 2 * BN;                          // 2 tile buffers x (main + corr)
+  // TMEM columns of one tile buffer.  BN = 128 / 16: main + corr.  BN = 64: [main | corr1] interleaved per CTA half
+  // (128 columns, written by ONE N = 128 MMA whose B operand is the hi plane followed by the lo plane) + corr2 (64).
+  static constexpr int TBUF = BN == 64 ? 192 : 2 * BN;
+  static constexpr int TMEM_NEED = 2 * TBUF;                            // 2 tile buffers
   static constexpr int NB = NB_FIT < I5_MAX_NB ? NB_FIT : I5_MAX_NB;
   static constexpr int SMEM = 1024 + 2 * I5_A_BUF + I5_OUT_BYTES + NB * B_STAGE + I5_BAR_BYTES;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -458,8 +461,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u, 63);       // both epilogues drained this buffer
         if (tr) w_tempty += clock64() - tw1;
         tc_fence_after();
-        const uint32_t t_main = tmem_base + (uint32_t)(buf * 2 * BN);
-        const uint32_t t_corr = t_main + (uint32_t)BN;
+        const uint32_t t_main = tmem_base + (uint32_t)(buf * Cfg::TBUF);
+        const uint32_t t_corr = t_main + (uint32_t)(BN == 64 ? 128 : BN);
         int kc = ks / 9;                         // K-chunk of unit t (t = kc * 9 + tap)
         uint32_t started = 0;                    // 0 until the first MMA of this segment has initialised the accumulators
 #pragma unroll 1
@@ -495,12 +498,28 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t a_t = a_word + (uint32_t)(dy * (I5_PITCH >> 4) + (tap - 3 * dy) * 8);   // halo coords of the tap
             const uint32_t b_t = b_word0 + (uint32_t)bs * (uint32_t)(Cfg::B_STAGE >> 4);
             if (!(prm.knob & 4)) {
+              if constexpr (BN == 64) {
+                // An M = 256, N = 64 MMA reads 5 KB of shared memory per SM in 32 tensor cycles (160 B/clk against the
+                // 128 B/clk the SM has): three of them per K step were shared-memory bound (57 cycles each, measured).
+                // The two products that share the hi plane of A become ONE N = 128 MMA - B = this CTA's 32 hi rows
+                // followed by its 32 lo rows, which are adjacent in the stage - so A_hi is read once: 11 KB per K step
+                // for 96 tensor cycles.  Columns: [0,32) hi.hi and [32,64) hi.lo of the leader's channels, [64,128) the
+                // same of the peer's; lo.hi goes to its own 64 columns.
+                constexpr uint32_t idesc_wide = make_idesc_bf16(2 * I5_BM, 128, 0, 0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t acc = started | (uint32_t)(k > 0);
-                i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
-                i5_umma2(t_corr, a_t + 2 * k, HI_A, b_t + B_LO_PLANE + 2 * k, HI_B, idesc, 1u);
-                i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = started | (uint32_t)(k > 0);
+                  i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+                  i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc_wide, acc);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = started | (uint32_t)(k > 0);
+                  i5_umma2(t_corr, a_t + A_LO_PLANE + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+                  i5_umma2(t_corr, a_t + 2 * k, HI_A, b_t + B_LO_PLANE + 2 * k, HI_B, idesc, 1u);
+                  i5_umma2(t_main, a_t + 2 * k, HI_A, b_t + 2 * k, HI_B, idesc, acc);
+                }
               }
             }
             started = 1u;
@@ -592,8 +611,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         w_tfull += clock64() - tw5;
       }
       tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
-      const uint32_t t_corr = t_main + (uint32_t)BN;
+      const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::TBUF);
+      const uint32_t t_corr = t_main + (uint32_t)(BN == 64 ? 128 : BN);
       const bool staged = owner && prm.tma_out;
       if constexpr (BN == 16) {
         // narrow tile (data gradient of the 3-channel first layer, N padded 3 -> 16): main and corr are adjacent
@@ -654,18 +673,30 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           for (int j = 0; j < 8; ++j) pv[j] = __ldcg(src + (size_t)j * I5_BM);
         }
         uint32_t rm[32], rc[32];
-        tmem_ld_32x32(t_main + (uint32_t)c, rm);
-        tmem_ld_32x32(t_corr + (uint32_t)c, rc);
-        tmem_ld_wait();
+        float v[32];
+        if constexpr (BN == 64) {                // main / corr1 of channels c..c+31 sit at columns 2c / 2c + 32, corr2 at c
+          tmem_ld_32x32(t_main + (uint32_t)(2 * c), rm);
+          tmem_ld_32x32(t_main + (uint32_t)(2 * c + 32), rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+          tmem_ld_32x32(t_corr + (uint32_t)c, rm);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rm[j]);
+        } else {
+          tmem_ld_32x32(t_main + (uint32_t)c, rm);
+          tmem_ld_32x32(t_corr + (uint32_t)c, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
+        }
         if (c + 64 >= BN) {                      // this warp's last TMEM read of the buffer: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) i5_arrive_cta(&tmem_empty_bar[buf], 0);     // the leader's barrier collects 16 arrivals
         }
         if ((prm.knob & 2) && owner) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
         if (npeer > 0) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

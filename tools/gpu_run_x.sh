@@ -1,0 +1,16 @@
+#!/bin/bash
+# BN=64: hi.hi and hi.lo merged into one N=128 MMA
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+run() { local name=$1; shift; timeout 600 python -m pytest "$@" -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "$name exit $?"; tail -n 3 gpurun_out/$name.log; grep -E "^(FAILED|ERROR)|^E  |watchdog" gpurun_out/$name.log | head -n 30; }
+run x_units tests/test_gpu_vgg_units.py -k "ph or fused or inference"
+run x_pipe tests/test_gpu_pipeline.py -k "not simt"
+run x_full tests/test_gpu_fullsize_properties.py
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/x_bench.json 2> gpurun_out/x_bench.err
+echo "bench exit $?"
+python - <<PY
+import json
+d = json.loads(open("gpurun_out/x_bench.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value", "ms_per_step", "kernel_ms_per_step")}, d["e2e"]["value"], d["with_cached_content_targets"]["value"])
+PY
+SMB_CONV_IMPL=ph timeout 300 python tools/gpu_conv_probe.py 2>> gpurun_out/x_probe.err | tee gpurun_out/x_probe.jsonl | cut -c1-600
