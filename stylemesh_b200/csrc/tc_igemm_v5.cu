@@ -51,8 +51,14 @@ struct I5Cfg {
   static constexpr int NB_FIT = (I5_SMEM_LIMIT - 1024 - 2 * I5_A_BUF - I5_OUT_BYTES - I5_BAR_BYTES) / B_STAGE;
   // TMEM columns of one tile buffer.  BN = 128 / 16: main + corr.  BN = 64: [main | corr1] interleaved per CTA half
   // (128 columns, written by ONE N = 128 MMA whose B operand is the hi plane followed by the lo plane) + corr2 (64).
-  static constexpr int TBUF = BN == 64 ? 192 : 2 * BN;
-  static constexpr int TMEM_NEED = 2 * TBUF;                            // 2 tile buffers
+  // (WIDE64 trades the third MMA of a K step for 64 more columns; measured 71 -> 68 us on conv1_2, so the 64-channel
+  // layers are not bound by shared-memory reads alone.  The default keeps main + corr = 128 columns and uses the
+  // freed TMEM for FOUR tile buffers: with 9 taps of N = 64 per tile (1.8 us of MMAs) the commit -> epilogue ->
+  // remote-arrive round trip of a buffer is longer than the MMAs of the one other tile a double buffer can hide.)
+  static constexpr bool WIDE64 = false;
+  static constexpr int TBUF = (BN == 64 && WIDE64) ? 192 : 2 * BN;
+  static constexpr int NT = (BN == 64 && !WIDE64) ? 4 : 2;              // tile buffers in TMEM
+  static constexpr int TMEM_NEED = NT * TBUF;
   static constexpr int NB = NB_FIT < I5_MAX_NB ? NB_FIT : I5_MAX_NB;
   static constexpr int SMEM = 1024 + 2 * I5_A_BUF + I5_OUT_BYTES + NB * B_STAGE + I5_BAR_BYTES;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -267,9 +273,9 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* a_empty = a_full + 2;                             // [2]  both CTAs
   uint64_t* b_full = a_empty + 2;                             // [NB] used in the leader
   uint64_t* b_empty = b_full + I5_MAX_NB;                     // [NB] both CTAs
-  uint64_t* tmem_full_bar = b_empty + I5_MAX_NB;              // [2]  both CTAs
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;               // [2]  used in the leader
-  uint64_t* f_land = tmem_empty_bar + 2;                      // [2]  both CTAs: own halo of a MASKED fused chunk has landed
+  uint64_t* tmem_full_bar = b_empty + I5_MAX_NB;              // [4]  both CTAs
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;               // [4]  used in the leader
+  uint64_t* f_land = tmem_empty_bar + 4;                      // [2]  both CTAs: own halo of a MASKED fused chunk has landed
   uint64_t* a_masked = f_land + 2;                            // [2]  used in the leader: both halos landed and masked
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_masked + 2);
 
@@ -303,10 +309,12 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
-      mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 16);     // 8 epilogue warps of each CTA
       mbar_init(&f_land[s], 1);
       mbar_init(&a_masked[s], 4);            // 2 mask warps of each CTA
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 16);     // 8 epilogue warps of each CTA
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&b_full[s], 1);
@@ -455,14 +463,14 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       while (w < w1) {
         const int ks = w % tpt;
         const int ke = (w1 - w < tpt - ks) ? ks + (w1 - w) : tpt;
-        const int buf = seg & 1;
-        const uint32_t use = (uint32_t)(seg >> 1);
+        const int buf = seg % Cfg::NT;
+        const uint32_t use = (uint32_t)(seg / Cfg::NT);
         const long long tw1 = tr ? clock64() : 0;
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u, 63);       // both epilogues drained this buffer
         if (tr) w_tempty += clock64() - tw1;
         tc_fence_after();
         const uint32_t t_main = tmem_base + (uint32_t)(buf * Cfg::TBUF);
-        const uint32_t t_corr = t_main + (uint32_t)(BN == 64 ? 128 : BN);
+        const uint32_t t_corr = t_main + (uint32_t)((BN == 64 && Cfg::WIDE64) ? 128 : BN);
         int kc = ks / 9;                         // K-chunk of unit t (t = kc * 9 + tap)
         uint32_t started = 0;                    // 0 until the first MMA of this segment has initialised the accumulators
 #pragma unroll 1
@@ -498,7 +506,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t a_t = a_word + (uint32_t)(dy * (I5_PITCH >> 4) + (tap - 3 * dy) * 8);   // halo coords of the tap
             const uint32_t b_t = b_word0 + (uint32_t)bs * (uint32_t)(Cfg::B_STAGE >> 4);
             if (!(prm.knob & 4)) {
-              if constexpr (BN == 64) {
+              if constexpr (BN == 64 && Cfg::WIDE64) {
                 // An M = 256, N = 64 MMA reads 5 KB of shared memory per SM in 32 tensor cycles (160 B/clk against the
                 // 128 B/clk the SM has): three of them per K step were shared-memory bound (57 cycles each, measured).
                 // The two products that share the hi plane of A become ONE N = 128 MMA - B = this CTA's 32 hi rows
@@ -569,8 +577,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const long long left = u1 - u;
       const int ke = (left < (long long)(tpt - ks)) ? ks + (int)left : tpt;
       const bool owner = (ks == 0);
-      const int buf = seg & 1;
-      const uint32_t use = (uint32_t)(seg >> 1);
+      const int buf = seg % Cfg::NT;
+      const uint32_t use = (uint32_t)(seg / Cfg::NT);
       const int n_tile = tile % prm.tiles_n;
       const int m_tile = 2 * (tile / prm.tiles_n) + (int)rank;
       const int y0 = (m_tile / prm.tiles_x) * I5_TH, x0 = (m_tile % prm.tiles_x) * I5_TW;
@@ -612,7 +620,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::TBUF);
-      const uint32_t t_corr = t_main + (uint32_t)(BN == 64 ? 128 : BN);
+      const uint32_t t_corr = t_main + (uint32_t)((BN == 64 && Cfg::WIDE64) ? 128 : BN);
       const bool staged = owner && prm.tma_out;
       if constexpr (BN == 16) {
         // narrow tile (data gradient of the 3-channel first layer, N padded 3 -> 16): main and corr are adjacent
@@ -674,7 +682,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         uint32_t rm[32], rc[32];
         float v[32];
-        if constexpr (BN == 64) {                // main / corr1 of channels c..c+31 sit at columns 2c / 2c + 32, corr2 at c
+        if constexpr (BN == 64 && Cfg::WIDE64) {  // main / corr1 of channels c..c+31 sit at columns 2c / 2c + 32, corr2 at c
           tmem_ld_32x32(t_main + (uint32_t)(2 * c), rm);
           tmem_ld_32x32(t_main + (uint32_t)(2 * c + 32), rc);
           tmem_ld_wait();
