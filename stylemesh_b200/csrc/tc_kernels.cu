@@ -197,7 +197,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::SLACK);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint64_t* masked_bar = tmem_full_bar + 1;              // [STAGES] count 128: masked pixel rows of B are zeroed
+  uint64_t* masked_bar = tmem_full_bar + 1;              // [STAGES] count 4: masked pixel rows of B are zeroed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(masked_bar + Cfg::STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +215,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&masked_bar[s], 128);
+      mbar_init(&masked_bar[s], 4);         // one arrival per mask warp
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -301,18 +301,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const int stage = it % Cfg::STAGES;
         const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
         mbar_wait(&full_bar[stage], phase, 14);
-        if (m == 0.f) {
-          // (ALIAS: A and B are the same bytes - zeroing the pixel in both operands is still m_p, m in {0,1})
-          uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + pl * 128 +
-                          (ALIAS ? plane * Cfg::A_BYTES : 2 * Cfg::A_BYTES + plane * Cfg::B_BYTES);
+        // most stages have no masked pixel at all (masks are contiguous regions): no store, no proxy fence then
+        if (__any_sync(0xffffffffu, m == 0.f)) {
+          if (m == 0.f) {
+            // (ALIAS: A and B are the same bytes - zeroing the pixel in both operands is still m_p, m in {0,1})
+            uint8_t* rowp = smem + stage * Cfg::STAGE_BYTES + pl * 128 +
+                            (ALIAS ? plane * Cfg::A_BYTES : 2 * Cfg::A_BYTES + plane * Cfg::B_BYTES);
 #pragma unroll
-          for (int g = 0; g < BN / 64; ++g)
+            for (int g = 0; g < BN / 64; ++g)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(rowp + g * GR_BOX_BYTES + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(rowp + g * GR_BOX_BYTES + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&masked_bar[stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&masked_bar[stage]);
         m = m_next;
       }
     }
