@@ -381,7 +381,7 @@ def run_ours(args):
     # ------------------------------------------------ CPU baseline (oracle port) -------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_oracle(args, budget_s=args.cpu_budget_s, max_steps=8)
+        cpu = run_cpu_oracle(args, budget_s=args.cpu_budget_s, max_steps=30)     # ~20 s of CPU work
 
     if world > 1:
         dist.barrier()
