@@ -86,10 +86,26 @@ def load_scene_into_store(scene: SceneBase, device, resize_size, min_pyramid_dep
     return store
 
 
+class _RandomOrderLoader:
+    """SubsetRandomSampler semantics (data/abstract_dataset.py:474-475): a fresh permutation of the indices every time
+    the loader is iterated (once per epoch); torch's global generator, like the reference's sampler."""
+
+    def __init__(self, store: ViewStore, indices):
+        self.store, self.indices = store, list(indices)
+
+    def __len__(self) -> int:
+        return len(self.indices)
+
+    def __iter__(self):
+        import torch
+        for j in torch.randperm(len(self.indices)).tolist():
+            yield self.store[self.indices[j]]
+
+
 class ViewStoreDataModule(LightningDataModule):
     """`*_Single_Scene_DataModule` (data/scannet_single_scene_dataset.py:15-64, data/matterport_single_scene_dataset.py:
     15-69) on a ViewStore: the scene is read and prepared once in setup(); the loaders hand out resident device batches
-    (sampler modes 'repeat' and 'sequential'; sequential train / val split, data/abstract_dataset.py:461-470)."""
+    (sampler modes 'repeat', 'sequential' and 'random'; sequential train / val split, data/abstract_dataset.py:461-470)."""
 
     def __init__(self, args, open_scene: Callable[[object], SceneBase], device=None):
         self.args = args
@@ -126,8 +142,9 @@ class ViewStoreDataModule(LightningDataModule):
             return self.store.batches(self.train_indices, a.index_repeat)
         if a.sampler_mode == "sequential":
             return self.store.batches(range(len(self.store)), 1)           # SequentialSampler(train_dataset)
-        raise ValueError(f"Unsupported sampler mode: {a.sampler_mode} ('random' needs a per-epoch permutation: use "
-                         f"--shuffle with 'repeat' or 'sequential')")
+        if a.sampler_mode == "random":
+            return _RandomOrderLoader(self.store, self.train_indices)      # SubsetRandomSampler(train_indices)
+        raise ValueError(f"Unsupported sampler mode: {a.sampler_mode}")
 
     def val_dataloader(self):
         return self.store.batches(self.val_indices, 1) if self.val_indices else None

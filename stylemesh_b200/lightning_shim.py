@@ -144,9 +144,17 @@ class Trainer:
             dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
 
     def _my_batches(self, loader):
-        """(batch_idx, batch) of this rank: view sharding, rank r owns views r, r+N, ..."""
+        """(batch_idx, batch) of this rank: view sharding, rank r owns views r, r+N, ...  Every rank must take the same
+        number of optimiser steps (the gradient exchange is collective), so an incomplete last group of fewer than
+        world_size batches is dropped (Lightning's DistributedSampler pads it by repeating samples instead)."""
+        limit = None
+        if self.world_size > 1 and hasattr(loader, "__len__"):
+            n = len(loader)
+            if 0 <= self.limit_train_batches < n:
+                n = self.limit_train_batches
+            limit = (n // self.world_size) * self.world_size
         for batch_idx, batch in enumerate(loader):
-            if 0 <= self.limit_train_batches <= batch_idx:
+            if 0 <= self.limit_train_batches <= batch_idx or (limit is not None and batch_idx >= limit):
                 break
             if batch_idx % self.world_size != self.rank:
                 continue

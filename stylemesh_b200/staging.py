@@ -119,6 +119,8 @@ class BatchStager:
 
     def stage(self, batch):
         """Issue the H2D copy of `batch` (nested tensors or a PackedBatch) on the copy stream; returns a ticket."""
+        if not isinstance(batch, PackedBatch) and self._resident(batch):
+            return None, batch                     # e.g. a ViewStore batch: already in HBM, nothing to copy or order
         slot = self._slots[self._next]
         self._next = (self._next + 1) % len(self._slots)
         with torch.cuda.stream(self.copy_stream):
@@ -151,13 +153,21 @@ class BatchStager:
         slot.used = True
         return slot, staged
 
+    def _resident(self, batch) -> bool:
+        tensors: List[torch.Tensor] = []
+        keep: List[bool] = []
+        _flatten(batch, tensors, keep)
+        return bool(tensors) and all(k or (t.is_cuda and t.device == self.device) for t, k in zip(tensors, keep))
+
     def acquire(self, ticket):
         """Make the current stream wait for the ticket's copy; returns the device-side batch."""
         slot, staged = ticket
-        torch.cuda.current_stream(self.device).wait_event(slot.ready)
+        if slot is not None:
+            torch.cuda.current_stream(self.device).wait_event(slot.ready)
         return staged
 
     def release(self, ticket) -> None:
         """Call after the step's kernels have been enqueued on the current stream."""
         slot, _ = ticket
-        slot.done.record(torch.cuda.current_stream(self.device))
+        if slot is not None:
+            slot.done.record(torch.cuda.current_stream(self.device))

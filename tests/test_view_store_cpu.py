@@ -73,6 +73,11 @@ def test_datamodule_split_and_sampler(gold, tmp_path, monkeypatch):
     assert dm.train_indices == [0, 1] and dm.val_indices == [2]
     assert [int(b[8][0]) for b in dm.train_dataloader()] == [0, 0, 1, 1]
     assert [int(b[8][0]) for b in dm.val_dataloader()] == [2]
+    args.sampler_mode = "random"                     # SubsetRandomSampler: a permutation of the train indices per epoch
+    torch.manual_seed(0)
+    loader = dm.train_dataloader()
+    epochs = [sorted(int(b[8][0]) for b in loader) for _ in range(3)]
+    assert len(loader) == 2 and all(e == [0, 1] for e in epochs)
 
 
 def test_matterport_region_matches_the_reference(tmp_path, monkeypatch):
@@ -90,3 +95,21 @@ def test_matterport_region_matches_the_reference(tmp_path, monkeypatch):
     store = load_scene_into_store(reg, "cpu", 30, min_pyramid_depth=1.0)
     for i in range(3):
         vsu.check_view_against_golden(store[i], gold, i)
+
+
+def test_trainer_gives_every_rank_the_same_number_of_steps():
+    """View sharding (rank r owns batches r, r+N, ...): an incomplete last group is dropped so that the collective
+    gradient exchange never waits for a rank that has run out of views."""
+    from stylemesh_b200.lightning_shim import Trainer
+    loader = list(range(11))
+    counts = []
+    for rank in range(4):
+        t = Trainer.__new__(Trainer)
+        t.world_size, t.rank, t.limit_train_batches = 4, rank, -1
+        mine = [i for i, _ in t._my_batches(loader)]
+        counts.append(len(mine))
+        assert mine == [rank, rank + 4]
+    assert counts == [2, 2, 2, 2]
+    t = Trainer.__new__(Trainer)
+    t.world_size, t.rank, t.limit_train_batches = 1, 0, 5
+    assert [i for i, _ in t._my_batches(loader)] == [0, 1, 2, 3, 4]
