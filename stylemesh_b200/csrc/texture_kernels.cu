@@ -301,13 +301,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// thread p < world waits until rank p has published `epoch` in this rank's flag slot; ~2 s watchdog, then trap
+// thread p < world waits until rank p has published `epoch` in this rank's flag slot.  Ranks may be seconds apart at
+// the first step (one-off style-target pass, allocations), so the watchdog is generous: ~30 s, then trap
 __device__ __forceinline__ void dist_wait_all(const unsigned int* my_flags, int world, unsigned int epoch, int what) {
   if ((int)threadIdx.x < world) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {
       __nanosleep(200);
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > 60000000000LL) {
         printf("[smb] dist_adam watchdog: phase %d, block %d waiting for rank %d (epoch %u)\n", what, (int)blockIdx.x,
                (int)threadIdx.x, epoch);
         asm volatile("trap;");
