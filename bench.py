@@ -460,11 +460,18 @@ def run_reference(args):
 def main():
     args = parse_args()
     # exactly ONE JSON line on stdout: library / reference-style prints ("Use style image pyramid ...") go to stderr
+    # (also at file-descriptor level: NCCL writes its "NCCL version ..." banner straight to fd 1)
     real_stdout = sys.stdout
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     try:
         line = run_reference(args) if args.impl == "reference" else run_ours(args)
     finally:
+        sys.stderr.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
         sys.stdout = real_stdout
     if line is not None:
         print(json.dumps(line), flush=True)
