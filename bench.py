@@ -181,7 +181,9 @@ def ncu_traffic_per_launch():
         val, unit = txt.split()[:2]
         return float(val.replace(",", "")) * units[unit]
 
-    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "*ncu_full*ph*.json")), reverse=True):
+    paths = glob.glob(os.path.join(REPO, "profiles", "*ncu_full*ph*.json")) + \
+        glob.glob(os.path.join(REPO, "profiles", "*ncu_full_step*.json"))
+    for path in sorted(paths, key=os.path.basename, reverse=True):       # newest round tag first
         try:
             rows = [r for r in json.load(open(path)) if "igemm_ph_kernel" in r.get("Kernel Name", "")]
             tot = [to_bytes(r["dram__bytes_read.sum"]) + to_bytes(r["dram__bytes_write.sum"]) for r in rows]
