@@ -50,7 +50,9 @@ class ScanNetScene(SceneBase):
         self.colors = _numeric_sorted(join(scene_path, "color"), lambda f: f.endswith(("jpg", "png")))
         sensor = _numeric_sorted(join(scene_path, "depth"), lambda f: True)
         rendered = _numeric_sorted(join(scene_path, "uv"), lambda f: "npy" in f and "depth" in f)
-        self.rendered_depth = len(sensor) == 0
+        self.rendered_depth = len(sensor) == 0                     # an EMPTY depth/ folder selects the rendered depth;
+        if not isdir(join(scene_path, "depth")):                   # a missing one makes the scene incomplete (:128-131)
+            rendered = []
         self.depths = rendered if self.rendered_depth else sensor
         self.poses = _numeric_sorted(join(scene_path, "pose"), lambda f: True)
         self.angles = _numeric_sorted(join(scene_path, "uv"), lambda f: "npy" in f and "angle" in f)

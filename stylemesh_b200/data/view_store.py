@@ -81,14 +81,13 @@ class ViewStore:
         W, H = self.size_wh
         if len(raw.uv_pyramid) != len(self.levels):
             raise ValueError(f"expected {len(self.levels)} UV pyramid levels, got {len(raw.uv_pyramid)}")
-        rgb = np.asarray(raw.rgb)
-        rgb = np.array(rgb, order="C", copy=not rgb.flags.writeable)
+        rgb = _owned(raw.rgb)
         if rgb.dtype != np.uint8 or rgb.shape != (H, W, 3):
             raise ValueError(f"rgb must be uint8 of shape {(H, W, 3)} (resized by the reader), got {rgb.dtype} {rgb.shape}")
         depth = np.asarray(raw.depth)
         if depth.ndim == 3:
             depth = depth[:, :, 0]
-        depth = np.array(depth, order="C", copy=not depth.flags.writeable)      # PIL hands out read-only buffers
+        depth = _owned(depth)
         if depth.dtype not in (np.uint16, np.float64, np.float32):
             raise ValueError(f"depth must be uint16, float64 or float32, got {depth.dtype}")
         depth_is_f32 = depth.dtype == np.float32
@@ -150,6 +149,13 @@ class ViewStore:
     def batches(self, indices: Sequence[int], index_repeat: int = 1) -> List[tuple]:
         """The order of RepeatingSampler (data/abstract_dataset.py:498-505): each index `index_repeat` times in a row."""
         return [self._views[i] for i in indices for _ in range(max(1, int(index_repeat)))]
+
+
+def _owned(a) -> np.ndarray:
+    """C-contiguous and writable (PIL hands out read-only buffers, channel slices are strided): what torch.from_numpy
+    wants."""
+    a = np.ascontiguousarray(a)
+    return a if a.flags.writeable else a.copy()
 
 
 def _tensors_of(obj):

@@ -70,6 +70,47 @@ def write_scene(root):
     return os.path.join(root, "train", "images"), raw
 
 
+RD_SCENE = "scene0001_00"
+
+
+def write_rendered_depth_scene(root):
+    """ScanNet layout whose depth/ folder is EMPTY: the reference then reads the renderer's float32
+    `uv/<i>.rendered_depth.npy` (data/scannet_dataset.py:117-144, 303-304) and keeps numpy's float32 arithmetic in
+    calculate_depth_level."""
+    from PIL import Image
+    rng = np.random.default_rng(17)
+    sp = os.path.join(root, "train", "images", RD_SCENE)
+    for d in ["color", "depth", "pose", "uv", "uv_32", "uv_48"]:
+        os.makedirs(os.path.join(sp, d))
+    with open(os.path.join(sp, RD_SCENE + ".txt"), "w") as f:
+        f.write("colorHeight = 60\ncolorWidth = 80\nfx_color = 70.5\nfy_color = 71.25\nmx_color = 39.5\nmy_color = 29.5\n")
+    raw = {}
+    for i in range(2):
+        H, W = COLOR_HW
+        rgb = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        Image.fromarray(rgb).save(os.path.join(sp, "color", f"{i}.png"))
+        np.savetxt(os.path.join(sp, "pose", f"{i}.txt"), np.eye(4), delimiter=" ")
+        hd, wd = 48, 64
+        yy, xx = np.meshgrid(np.arange(hd), np.arange(wd), indexing="ij")
+        dep = (0.25 + 2.4 * ((0.8 * xx / wd + 0.5 * yy / hd + 0.3 * i) % 1.0)).astype(np.float32)
+        dep[(xx + 3 * yy + i) % 29 == 0] = 0.0
+        dep3 = np.stack([dep, dep * 0, dep * 0], axis=2)
+        np.save(os.path.join(sp, "uv", f"{i}.rendered_depth.npy"), dep3)
+        raw[f"rd_rgb_{i}"], raw[f"rd_depth_{i}"] = rgb, dep3
+        for h in (32, 48):
+            w = h * 4 // 3
+            y2, x2 = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+            uv = np.stack([(0.1 + 0.8 * x2 / w).astype(np.float32), (0.1 + 0.8 * y2 / h).astype(np.float32),
+                           np.zeros((h, w), np.float32)], axis=2)
+            uv[(x2 + y2 + i) % 11 == 0] = 0.0
+            np.save(os.path.join(sp, f"uv_{h}", f"{i}.npy"), uv)
+            raw[f"rd_uv{h}_{i}"] = uv
+        ang = np.stack([(0.2 + 0.8 * rng.random((48, 64))).astype(np.float32)] * 3, axis=2)
+        np.save(os.path.join(sp, "uv", f"{i}.angle.npy"), ang)
+        raw[f"rd_angle_{i}"] = ang
+    return os.path.join(root, "train", "images"), raw
+
+
 MP_HOUSE = "house0"
 MP_NAMES = ["0e92a69a50414253_i0_0", "0e92a69a50414253_i1_2", "5b9b2794954e4694_i0_1"]   # sort: hash, camera*100 + yaw
 
@@ -167,6 +208,29 @@ def main():
                 out[f"ref_{n}_{i}"] = np.asarray(t)
     out["meta"] = np.asarray([N_VIEWS, RESIZE, len(ds.levels)], dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "view_prep.npz"), **out)
+
+    # rendered (float32) depth instead of sensor PNGs
+    rd_tmp = tempfile.mkdtemp(prefix="smb_view_golden_rd_")
+    rd_root, rd_raw = write_rendered_depth_scene(rd_tmp)
+    rd = DS(root_path=rd_root, scene=RD_SCENE, min_images=1, max_images=-1, transform_rgb=t_rgb, transform_label=t_label,
+            transform_uv=t_uv, resize_size=RESIZE, pyramid_levels=2, min_pyramid_depth=MIN_DEPTH, min_pyramid_height=32,
+            verbose=False)
+    assert rd.rendered_depth
+    ro = dict(rd_raw)
+    ro["levels"] = np.asarray(rd.levels, dtype=np.float64)
+    for i in range(len(rd)):
+        item = rd[i]
+        for n, t in zip(names, item):
+            if n == "uv":
+                for l, u in enumerate(t):
+                    ro[f"ref_uv{l}_{i}"] = np.asarray(u)
+            elif n == "idx":
+                ro[f"ref_idx_{i}"] = np.asarray(t)
+            else:
+                ro[f"ref_{n}_{i}"] = np.asarray(t)
+    ro["meta"] = np.asarray([len(rd), RESIZE, len(rd.levels)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "view_prep_rendered.npz"), **ro)
+    print("rendered-depth levels", ro["levels"], "views", len(rd), "depth dtype", ro["ref_depth_0"].dtype)
 
     # Matterport: same pipeline, other file layout, depth / 4000, mask without the depth factor
     mp_root, mp_raw = write_matterport(tmp)

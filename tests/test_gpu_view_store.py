@@ -39,6 +39,16 @@ def test_matterport_store_matches_reference_tuples(tmp_path):
         vsu.check_view_against_golden(store[i], mg, i)
 
 
+def test_rendered_depth_store_matches_reference_tuples(tmp_path):
+    from stylemesh_b200.data.scannet_scene import ScanNetScene, load_scene_into_store
+    rg = np.load(vsu.RD_GOLD)
+    root = vsu.write_rendered_depth_scene(rg, tmp_path)
+    sc = ScanNetScene(f"{root}/train/images/{vsu.RD_SCENE}", pyramid_levels=2, min_pyramid_height=32)
+    store = load_scene_into_store(sc, "cuda", 30, min_pyramid_depth=1.0)
+    for i in range(2):
+        vsu.check_view_against_golden(store[i], rg, i)
+
+
 def test_kernels_equal_the_oracle_on_ragged_sizes():
     """Each kernel against the pinned numpy oracle on sizes that are not multiples of anything; integer outputs,
     gathers and the explicitly rounded float arithmetic must be bit-identical."""

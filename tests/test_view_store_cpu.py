@@ -113,3 +113,19 @@ def test_trainer_gives_every_rank_the_same_number_of_steps():
     t = Trainer.__new__(Trainer)
     t.world_size, t.rank, t.limit_train_batches = 1, 0, 5
     assert [i for i, _ in t._my_batches(loader)] == [0, 1, 2, 3, 4]
+
+
+def test_rendered_depth_scene_matches_the_reference(tmp_path, monkeypatch):
+    """Empty depth/ folder -> the renderer's float32 depth maps (scannet_dataset.py:117-144, 303-304); numpy keeps
+    float32 arithmetic for uv_height there, and so do the oracle and the kernel."""
+    fake_engine.install(monkeypatch)
+    from stylemesh_b200.data.scannet_scene import ScanNetScene, load_scene_into_store
+    gold = np.load(vsu.RD_GOLD)
+    root = vsu.write_rendered_depth_scene(gold, tmp_path)
+    sc = ScanNetScene(f"{root}/train/images/{vsu.RD_SCENE}", pyramid_levels=2, min_pyramid_height=32)
+    assert sc.rendered_depth and len(sc) == 2 and sc.levels == [32.0, 48.0]
+    raw, _ = sc.load_raw(0, 30)
+    assert raw.depth.dtype == np.float32 and raw.depth_divisor == 1.0
+    store = load_scene_into_store(sc, "cpu", 30, min_pyramid_depth=1.0)
+    for i in range(2):
+        vsu.check_view_against_golden(store[i], gold, i)

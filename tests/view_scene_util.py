@@ -27,6 +27,28 @@ def write_scene(gold, root) -> str:
     return str(root)
 
 
+RD_SCENE = "scene0001_00"
+RD_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "view_prep_rendered.npz")
+
+
+def write_rendered_depth_scene(gold, root) -> str:
+    """ScanNet layout with an EMPTY depth/ folder and float32 `uv/<i>.rendered_depth.npy` files."""
+    from PIL import Image
+    sp = os.path.join(str(root), "train", "images", RD_SCENE)
+    for d in ["color", "depth", "pose", "uv", "uv_32", "uv_48"]:
+        os.makedirs(os.path.join(sp, d), exist_ok=True)
+    with open(os.path.join(sp, RD_SCENE + ".txt"), "w") as f:
+        f.write("colorHeight = 60\ncolorWidth = 80\nfx_color = 70.5\nfy_color = 71.25\nmx_color = 39.5\nmy_color = 29.5\n")
+    for i in range(int(gold["meta"][0])):
+        Image.fromarray(gold[f"rd_rgb_{i}"]).save(os.path.join(sp, "color", f"{i}.png"))
+        np.savetxt(os.path.join(sp, "pose", f"{i}.txt"), np.eye(4), delimiter=" ")
+        np.save(os.path.join(sp, "uv", f"{i}.rendered_depth.npy"), gold[f"rd_depth_{i}"])
+        np.save(os.path.join(sp, "uv", f"{i}.angle.npy"), gold[f"rd_angle_{i}"])
+        for h in (32, 48):
+            np.save(os.path.join(sp, f"uv_{h}", f"{i}.npy"), gold[f"rd_uv{h}_{i}"])
+    return str(root)
+
+
 MP_HOUSE = "house0"
 MP_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "view_prep_matterport.npz")
 
@@ -68,8 +90,9 @@ def check_view_against_golden(view, gold, i):
     assert np.array_equal(np_(t["rounded_depth_level"])[0], gold[f"ref_rounded_depth_level_{i}"])
     assert np.array_equal(np_(t["other_depth_level"])[0], gold[f"ref_other_depth_level_{i}"])
     assert t["rounded_depth_level"].dtype == torch.int64 and t["other_depth_level"].dtype == torch.int64
-    assert len(t["uv"]) == 3
-    for l in range(3):
+    nlev = int(gold["meta"][2])
+    assert len(t["uv"]) == nlev
+    for l in range(nlev):
         assert np.array_equal(np_(t["uv"][l])[0], gold[f"ref_uv{l}_{i}"])
     assert np.array_equal(np_(t["rgb"])[0], gold[f"ref_rgb_{i}"])
     assert np.array_equal(np_(t["angle_guidance"])[0], gold[f"ref_angle_guidance_{i}"])
