@@ -56,6 +56,9 @@ def parse_args():
                     help="reuse VGG(target) per view (SURVEY §8f.1); OFF for the headline number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of view 0 before timing")
+    ap.add_argument("--sustained-s", type=float, default=5.0,
+                    help="length of the sustained leg (same step looped, clocks/power sampled); 0 = skip")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc1", "pair", "halo", "ph", "simt"])
     return ap.parse_args()
@@ -110,7 +113,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
@@ -121,10 +124,15 @@ class ClockSampler:
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": statistics.median(pw) if pw else None, "power_w_max": max(pw) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -223,6 +231,12 @@ def run_ours(args):
     host_views = make_views(args, rank)
     dev_batches = [v.to(device).as_batch() for v in host_views]
     nv = len(dev_batches)
+
+    # ------------------------------------------------ parity gate: this workload vs the CPU oracle ------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_at_bench_config(args, mdl, host_views[0], dev_batches[0])
+    barrier()
 
     # ------------------------------------------------ value leg (device-resident inputs) ----------------------
     mdl.cache_view_plans = True                 # masks / counts of a resident view are inputs, built once
@@ -325,9 +339,53 @@ def run_ours(args):
     # nvidia-smi sampled every 100 ms from the start of the value leg to the end of the e2e leg (all timed regions)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ------------------------------------------------ sustained leg: the same step for >= 5 s ----------------
+    # The value leg is a ~40 ms burst at boost clocks; a real scene runs for minutes.  Loop the value leg's step until
+    # the wall clock says --sustained-s, device-timed, with clocks / power / throttle reasons sampled throughout.
+    sustained = None
+    if args.sustained_s > 0:
+        s_sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            s_sampler.start()
+        chunk = 100
+        n_chunks = torch.zeros(1, device=device)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        last0, last1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        s0.record()
+        done = 0
+        while True:
+            # every rank must run the same number of steps (one exchange per step): rank 0's clock decides
+            go = torch.tensor([1.0 if (time.perf_counter() - t_wall) < args.sustained_s else 0.0], device=device)
+            if world > 1:
+                dist.broadcast(go, 0)
+            if float(go) == 0.0 and done > 0:
+                break
+            last0.record()
+            for i in range(chunk):
+                one_step(mdl, opt, dev_batches[(done + i) % nv], done + i)
+            last1.record()
+            done += chunk
+            torch.cuda.current_stream().synchronize()      # keeps the host at most one chunk ahead of the device
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1), last0.elapsed_time(last1)], device=device)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        s_clk = s_sampler.stop() if rank == 0 else None
+        if rank == 0:
+            sustained = {"value": world * done / (float(sms[0]) / 1e3), "unit": UNIT, "steps": done,
+                         "seconds": float(sms[0]) / 1e3, "ms_per_step": float(sms[0]) / done,
+                         "ms_per_step_last_chunk": float(sms[1]) / chunk,
+                         "sm_mhz": s_clk["sm_mhz"], "sm_max_mhz": s_clk["sm_max_mhz"], "power_w": s_clk["power_w"],
+                         "power_w_max": s_clk["power_w_max"], "reasons": s_clk["reasons"],
+                         "clock_samples": s_clk.get("samples"),
+                         "note": "same step and inputs as `value`, looped back to back; one host sync per 100 steps"}
+
     # ------------------------------------------------ roofline pass (per-kernel-class events) ------------------
     # (every rank runs these steps — optimizer.step() all-reduces — but only rank 0 reports)
-    roof, kernel_ms, roof_hbm = None, None, None
+    roof, kernel_ms, roof_hbm, kernel_ms_note, kernel_share = None, None, None, None, None
     mdl.cache_view_plans = True
     vgg = mdl.vgg_loss.vgg.engine()
     nsteps = min(5, max(2, args.steps))
@@ -353,18 +411,41 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        # the roofline pass is a handful of steps at boost clocks (a burst window, like the value leg): divide by
+        # the BURST peak; the sustained leg's estimate below is divided by the sustained peak
+        peak_tf = float(peaks.get("bf16_tflops", 1690.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; the kernel is timed in a short window at boost clocks)" \
+            if peaks else "fallback 1.69 PFLOP/s burst"
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        class_total = sum(v["ms"] for v in t.values()) / nsteps
+        step_ms = total_ms / args.steps
         traffic, traffic_src = ncu_traffic_per_launch()
         roof = {"kernel": "igemm_ph_kernel (VGG conv forward + data-gradient launches)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "peak_regime": "burst",
                 "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms_per_step": conv_ms,
+                "kernel_share_of_step": conv_ms / max(class_total + opt_ms, 1e-9),
                 "executed_bf16_tflops": 3.0 * achieved,
                 "note": "achieved = fp32-equivalent algorithmic FLOPs (2*P*Cout*Cin*9 per launch); each is executed "
                         "as 3 bf16 tcgen05 MMAs (hi*hi+lo*hi+hi*lo) for fp32-grade parity, so frac <= 1/3 by "
                         "construction; executed_bf16_tflops/peak is the tensor-pipe fraction"}
+
+        if sustained is not None:
+            # same kernel share applied to the sustained step time, against the sustained cuBLAS peak
+            share = conv_ms / max(class_total + opt_ms, 1e-9)
+            sus_peak = float(peaks.get("bf16_tflops_sustained", 1405.0))
+            sus_tf = conv_fl / (share * sustained["ms_per_step"] * 1e-3) / 1e12
+            sustained["roofline"] = {"peak_regime": "sustained", "peak": sus_peak, "achieved_est": sus_tf,
+                                     "frac_est": sus_tf / sus_peak, "unit": "TFLOP/s",
+                                     "how": "algorithmic conv FLOPs / (kernel share of the step x sustained ms_per_step)"}
+        kernel_ms_note = ("per-class CUDA events are recorded around every launch in this pass, which serialises the "
+                          "programmatic-dependent-launch overlap between kernels: classes sum to "
+                          f"{class_total + opt_ms:.3f} ms against a {step_ms:.3f} ms step; read them as shares "
+                          "(kernel_share_per_step = class / sum), scaled_ms = share x ms_per_step")
+        tot = max(class_total + opt_ms, 1e-9)
+        kernel_share = {k: round(v["ms"] / nsteps / tot, 4) for k, v in t.items()}
+        kernel_share["optimizer"] = round(opt_ms / tot, 4)
 
         # the dominant HBM-bound kernel: the fused clamp + regulariser + Adam pass over the flat texture buffers
         # (N = 1: read p, g, m, v and write p, g, m, v = 32 B per element, 4 of them the gradient reset)
@@ -396,7 +477,9 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "host_enqueue_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (tensor-core convs/Gram as 3x bf16 split products, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roof, "roofline_hbm": roof_hbm, "kernel_ms_per_step": kernel_ms, "cpu_baseline": cpu, "with_cached_content_targets": cached,
+        "roofline": roof, "roofline_hbm": roof_hbm, "kernel_ms_per_step": kernel_ms, "kernel_ms_note": kernel_ms_note,
+        "kernel_share_per_step": kernel_share, "sustained": sustained, "parity_at_bench_config": parity,
+        "cpu_baseline": cpu, "with_cached_content_targets": cached,
         "impls": {"conv": os.environ.get("SMB_CONV_IMPL", "ph"), "gram": os.environ.get("SMB_GRAM_IMPL", "tc")},
     }
     return line
@@ -405,7 +488,8 @@ def run_ours(args):
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = None, warmup: int = 1):
+def build_oracle(args, layers=None, as_written=True):
+    """The CPU oracle (reference algorithm) on this bench's workload: same VGG weights, style image, flags and views."""
     from oracle import stylemesh_oracle as orc
     from stylemesh_b200 import synthetic as syn
     from stylemesh_b200.hostinfo import usable_cpus
@@ -417,13 +501,46 @@ def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = Non
     loss = orc.StyleContentOracle(vgg_params=sd, style_weights=list(preset["style_weights"]),
                                   angle_threshold=preset["angle_threshold"],
                                   style_pyramid_mode=preset["style_pyramid_mode"], gram_mode=preset["gram_mode"],
-                                  as_written=True)
+                                  as_written=as_written)
     loss.set_style_image(syn.make_style_image(7, sh, sw).unsqueeze(0))
-    torch.manual_seed(0)
-    layers = [torch.rand(3, args.texture // 2 ** i, args.texture // 2 ** i) for i in range(args.layers)]
+    if layers is None:
+        torch.manual_seed(0)
+        layers = [torch.rand(3, args.texture // 2 ** i, args.texture // 2 ** i) for i in range(args.layers)]
     cfg = orc.OracleConfig(use_angle_weight=preset["use_angle_weight"], use_depth_scaling=preset["use_depth_scaling"],
                            loss_weights=dict(preset["loss_weights"]), hierarchical=True, learning_rate=1.0)
-    pipe = orc.OraclePipeline(layers, loss, cfg)
+    return orc.OraclePipeline(layers, loss, cfg), cores
+
+
+def parity_at_bench_config(args, mdl, host_view, dev_batch):
+    """Teacher-forced check of THIS run's workload against the CPU oracle before anything is timed: the loss terms
+    and the dense texture gradient of view 0 at the bench's own texels (bars of tests/test_gpu_fullsize_parity.py)."""
+    from oracle import stylemesh_oracle as orc
+    t0 = time.perf_counter()
+    layers = [m.data.detach().cpu().clone() for m in mdl._layer_modules()]
+    pipe, _ = build_oracle(args, layers=layers, as_written=False)
+    want, want_grads = pipe.grads(host_view.as_batch())
+    buf = mdl.fused_view_step(dev_batch, want_grads=True).cpu()
+    got = {"style": float(buf[0]), "content": float(buf[1]), "tex_reg": float(buf[2]), "total": float(buf[3])}
+    relerr = {k: abs(got[k] - want[k]) / max(abs(want[k]), 1e-12) for k in got}
+    lam = float(mdl.loss_weights.get("tex_reg", 0.0))
+    grad_rel = []
+    for l, (g, gg) in enumerate(zip([g.cpu() for g in mdl._grad_tensors()], want_grads)):
+        x = pipe.layers[l].detach().clamp(orc.CLAMP_LO, orc.CLAMP_HI)
+        data_want = gg - lam * mdl.tex_reg_weights[l] * 2.0 * x / x.numel()       # ours adds the regulariser in Adam
+        grad_rel.append(float((g - data_want).norm() / data_want.norm().clamp_min(1e-30)))
+    mdl._ensure_fused_state()["grad"].zero_()
+    ok = all(v < 1e-3 for v in relerr.values()) and all(v < 1e-2 for v in grad_rel)
+    res = {"loss_rel_err": relerr, "grad_rel_l2_per_layer": grad_rel, "loss_ours": got, "loss_oracle": want,
+           "bars": {"loss": 1e-3, "grad_rel_l2": 1e-2}, "ok": ok, "seconds": time.perf_counter() - t0,
+           "what": "view 0, teacher-forced at the bench's initial texels, ours vs CPU oracle (as_written=False: "
+                   "same values, skips the reference's unused conv5_2..5_4)"}
+    if not ok:
+        raise SystemExit(f"[bench] PARITY FAILURE at the bench configuration: {json.dumps(res)}")
+    return res
+
+
+def run_cpu_oracle(args, budget_s: float, max_steps: int, fixed_steps: int = None, warmup: int = 1):
+    pipe, cores = build_oracle(args, as_written=True)
     views = [v.as_batch() for v in make_views(args, 0)]
     t0 = time.perf_counter()
     for i in range(warmup):

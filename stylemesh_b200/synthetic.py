@@ -188,12 +188,22 @@ PRESETS = {
 }
 
 
+# the reference's rendered UV pyramids (scripts/scannet/render_uvs.py:77-90,126-130: heights linspace(256, 784, 4),
+# widths from the sensor aspect ratio, rounded by the renderer driver) - SURVEY §8
+SCANNET_PYRAMID = [(256, 341), (432, 576), (608, 811), (784, 1045)]
+MATTERPORT_PYRAMID = [(256, 320), (432, 540), (608, 760), (784, 980)]
+
+
 def pyramid_sizes(base_hw: Tuple[int, int], levels: int, min_height: int = None) -> List[Tuple[int, int]]:
-    """UV pyramid sizes in the spirit of scripts/scannet/render_uvs.py:77-90,126-130: heights linearly spaced
-    from the base height to ~3x, widths scaled by the aspect ratio (ScanNet: 256x341 ... 784x1045)."""
+    """UV pyramid sizes of scripts/scannet/render_uvs.py:77-90,126-130: the reference's own ScanNet / Matterport
+    tables when the base size is theirs, else heights linearly spaced from the base height to ~3x with widths scaled
+    by the aspect ratio."""
     h0, w0 = base_hw
     if levels <= 1:
         return [(h0, w0)]
+    for table in (SCANNET_PYRAMID, MATTERPORT_PYRAMID):
+        if (h0, w0) == table[0] and levels <= len(table):
+            return list(table[:levels])
     out = []
     for i in range(levels):
         h = int(round(h0 + (h0 * 2.0625) * i / (levels - 1)))

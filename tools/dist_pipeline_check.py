@@ -1,0 +1,163 @@
+"""N-rank END-TO-END parity with the real kernels (run under torchrun on N GPUs of one box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29561 \
+        tools/dist_pipeline_check.py [--preset only2D --view 480x640 --texture 2048 --steps 3]
+
+Every rank runs the product pipeline (sample -> VGG -> losses -> backward -> scatter -> fused reduce-scatter + Adam +
+all-gather over NVLink peer memory) on ITS OWN view.  After every step rank 0 runs the CPU oracle's N-rank semantics
+(OraclePipeline.step_views: mean of the per-view gradients, regulariser once, one Adam step = Lightning-DDP mean,
+/root/reference/model/optimize.py:30 `Trainer` + SURVEY §8e) TEACHER-FORCED on the texels and Adam moments our ranks
+held before the step, and compares
+  * the mean of the per-rank loss terms            <= 1e-3 relative
+  * the texels after the step                      by distribution (median <= 1e-5, >= 95 % within 1e-3,
+                                                   <= 0.5 % sign-flipped)
+  * all replicas                                   bit-identical, gradient buffers zero.
+Prints one JSON line per step and a summary line on rank 0; exits non-zero on any failure.
+The oracle is used here as the checker only (tools/ is test infrastructure).
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--preset", default="only2D")
+ap.add_argument("--view", default="480x640")
+ap.add_argument("--texture", type=int, default=2048)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--out", default=None, help="append the JSON lines to this file as well")
+args = ap.parse_args()
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+from stylemesh_b200 import synthetic as syn                                                   # noqa: E402
+from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline               # noqa: E402
+
+preset = syn.PRESETS[args.preset]
+vh, vw = [int(x) for x in args.view.split("x")]
+sizes = syn.pyramid_sizes((vh, vw), preset["pyramid_levels"]) if preset["pyramid_levels"] > 1 else [(vh, vw)]
+nl = preset["hierarchical_layers"]
+sd = syn.make_vgg_state_dict(0, bias_scale=0.05)
+layers0 = syn.make_texture_layers(11, args.texture, args.texture, nl)
+style = syn.make_style_image(7, 384, 485)
+views = [syn.make_view(1000 + r, (vh, vw), sizes) for r in range(world)]
+
+tmp = tempfile.mkdtemp(prefix="smb_distcheck_")
+vgg_path = os.path.join(tmp, f"vgg_{rank}.pth")
+torch.save(sd, vgg_path)
+sys.stdout.flush()
+_real = sys.stdout
+sys.stdout = sys.stderr                    # the modules print reference-style banners
+mdl = TextureOptimizationStyleTransferPipeline(
+    args.texture, args.texture, hierarchical_texture=True, hierarchical_layers=nl, random_texture_init=True,
+    style_image=style.clone(), style_weights=list(preset["style_weights"]), vgg_gatys_model_path=vgg_path,
+    use_angle_weight=preset["use_angle_weight"], use_depth_scaling=preset["use_depth_scaling"],
+    style_pyramid_mode=preset["style_pyramid_mode"], gram_mode=preset["gram_mode"],
+    angle_threshold=preset["angle_threshold"], learning_rate=1.0, loss_weights=dict(preset["loss_weights"]),
+    save_texture=False)
+mdl.to(dev)
+with torch.no_grad():
+    for m, t in zip(mdl.texture.layers, layers0):
+        m.data.copy_(t.to(dev))
+(opt,), _ = mdl.configure_optimizers()
+st = mdl._ensure_fused_state()
+fused = bool(st.get("peer"))
+batch = views[rank].to(dev).as_batch()
+
+pipe = None
+if rank == 0:
+    from oracle import stylemesh_oracle as orc
+    loss = orc.StyleContentOracle(vgg_params=sd, style_weights=list(preset["style_weights"]),
+                                  angle_threshold=preset["angle_threshold"],
+                                  style_pyramid_mode=preset["style_pyramid_mode"], gram_mode=preset["gram_mode"],
+                                  as_written=False)
+    loss.set_style_image(style.unsqueeze(0))
+    cfg = orc.OracleConfig(use_angle_weight=preset["use_angle_weight"], use_depth_scaling=preset["use_depth_scaling"],
+                           loss_weights=dict(preset["loss_weights"]), hierarchical=True, learning_rate=1.0)
+    pipe = orc.OraclePipeline(layers0, loss, cfg)
+
+
+def emit(rec):
+    line = json.dumps(rec)
+    print(line, file=_real, flush=True)
+    if args.out:
+        with open(args.out, "a") as fh:
+            fh.write(line + "\n")
+
+
+def full_moments():
+    """the fused kernel shards the moments (rank r owns slice r, the rest of its buffers stays 0): sum = the full state"""
+    m, v = st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+    if fused:
+        dist.all_reduce(m)
+        dist.all_reduce(v)
+    return m.cpu(), v.cpu()
+
+
+ok_all = True
+for step in range(1, args.steps + 1):
+    # ---- state before the step (replicas identical) -> teacher-force the oracle on it
+    p_before = st["param"].clone().cpu()
+    m_before, v_before = full_moments()
+    # ---- our step
+    opt.zero_grad()
+    out = mdl.training_step(batch, step - 1)
+    out["loss"].backward()
+    opt.step()
+    torch.cuda.synchronize()
+    mine = mdl._loss_buf.clone()
+    all_l = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(all_l, mine)
+    p_after = st["param"].clone()
+    all_p = [torch.empty_like(p_after) for _ in range(world)]
+    dist.all_gather(all_p, p_after)
+    same = all(torch.equal(all_p[0], t) for t in all_p)
+    gzero = torch.tensor([float(st["grad"].abs().max())], device=dev)
+    dist.all_reduce(gzero, op=dist.ReduceOp.MAX)
+    ok = True
+    rec = None
+    if rank == 0:
+        with torch.no_grad():
+            for l, (t, (a, b)) in enumerate(zip(pipe.layers, st["spans"])):
+                t.copy_(p_before[a:b].view_as(t))
+                pipe.opt.state[t] = {"step": torch.tensor(float(step - 1)),
+                                     "exp_avg": m_before[a:b].view_as(t).clone(),
+                                     "exp_avg_sq": v_before[a:b].view_as(t).clone()}
+        want = pipe.step_views([v.as_batch() for v in views])
+        got = torch.stack(all_l).mean(0).cpu()
+        got = {"style": float(got[0]), "content": float(got[1]), "tex_reg": float(got[2]), "total": float(got[3])}
+        lrel = {k: abs(got[k] - want[k]) / max(abs(want[k]), 1e-12) for k in got}
+        tex = []
+        pa = p_after.cpu()
+        for l, (t, (a, b)) in enumerate(zip(pipe.layers, st["spans"])):
+            o, w = pa[a:b].view_as(t), t.detach()
+            d = (o - w).abs()
+            tex.append({"layer": l, "frac_off_gt_1e-3": (d > 1e-3 * w.abs().clamp_min(1.0)).float().mean().item(),
+                        "frac_flipped": (d > 0.1).float().mean().item(), "median_abs": d.median().item()})
+        ok = (all(v < 1e-3 for v in lrel.values()) and same and float(gzero) == 0.0 and
+              all(x["frac_off_gt_1e-3"] <= 5e-2 and x["frac_flipped"] <= 5e-3 and x["median_abs"] <= 1e-5 for x in tex))
+        rec = {"kind": "dist_pipeline_step", "world": world, "step": step, "fused_dist_adam": fused,
+               "loss_rel_err_mean_over_ranks": lrel, "texels": tex, "replicas_bit_identical": same,
+               "grad_buffers_zero": float(gzero) == 0.0, "ok": ok}
+        emit(rec)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.broadcast(flag, 0)
+    ok_all = ok_all and bool(flag.item() == 1.0)
+
+if rank == 0:
+    emit({"kind": "dist_pipeline_summary", "world": world, "preset": args.preset, "view": args.view,
+          "pyramid": sizes, "texture": args.texture, "steps": args.steps, "fused_dist_adam": fused, "ok": ok_all})
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok_all else 1)
