@@ -529,9 +529,13 @@ def parity_at_bench_config(args, mdl, host_view, dev_batch):
         data_want = gg - lam * mdl.tex_reg_weights[l] * 2.0 * x / x.numel()       # ours adds the regulariser in Adam
         grad_rel.append(float((g - data_want).norm() / data_want.norm().clamp_min(1e-30)))
     mdl._ensure_fused_state()["grad"].zero_()
-    ok = all(v < 1e-3 for v in relerr.values()) and all(v < 1e-2 for v in grad_rel)
-    res = {"loss_rel_err": relerr, "grad_rel_l2_per_layer": grad_rel, "loss_ours": got, "loss_oracle": want,
-           "bars": {"loss": 1e-3, "grad_rel_l2": 1e-2}, "ok": ok, "seconds": time.perf_counter() - t0,
+    # gate: the loss bar of north_star; the gradient is reported against the fp32 oracle and gated only against gross
+    # error - the fp32 oracle itself is 0.5 % (C2) .. 1.4 % (C4) away from the exact (float64) gradient, which is what
+    # tests/test_gpu_fullsize_parity.py measures both sides against (profiles/r02_gradient_noise_floor.md)
+    ok = all(v < 1e-3 for v in relerr.values()) and all(v < 5e-2 for v in grad_rel)
+    res = {"loss_rel_err": relerr, "grad_rel_l2_per_layer_vs_fp32_oracle": grad_rel, "loss_ours": got,
+           "loss_oracle": want, "bars": {"loss": 1e-3, "grad_rel_l2_gross": 5e-2}, "ok": ok,
+           "seconds": time.perf_counter() - t0,
            "what": "view 0, teacher-forced at the bench's initial texels, ours vs CPU oracle (as_written=False: "
                    "same values, skips the reference's unused conv5_2..5_4)"}
     if not ok:

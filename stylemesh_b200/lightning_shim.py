@@ -49,19 +49,25 @@ class _ScalarLog:
         self._pending.clear()
 
 
+def next_log_version(save_dir: str) -> int:
+    root = os.path.join(save_dir, "lightning_logs")
+    if not os.path.isdir(root):
+        return 0
+    olds = [int(d.split("_")[1]) for d in os.listdir(root) if d.startswith("version_") and d.split("_")[1].isdigit()]
+    return max(olds) + 1 if olds else 0
+
+
 class _Logger:
-    def __init__(self, save_dir: str = ".", version: Optional[int] = None):
+    """lightning_logs/version_N like the TensorBoardLogger the reference gets from Lightning (optimize.py:31).  Only
+    rank 0 writes; the other ranks share its version number and keep a sink."""
+
+    def __init__(self, save_dir: str = ".", version: Optional[int] = None, writer: bool = True):
         self.save_dir = save_dir
-        root = os.path.join(save_dir, "lightning_logs")
         if version is None:
-            version = 0
-            if os.path.isdir(root):
-                olds = [int(d.split("_")[1]) for d in os.listdir(root) if d.startswith("version_") and
-                        d.split("_")[1].isdigit()]
-                version = max(olds) + 1 if olds else 0
+            version = next_log_version(save_dir)
         self.version = version
-        self.log_dir = os.path.join(root, f"version_{version}")
-        self.experiment = _ScalarLog(os.path.join(self.log_dir, "scalars.jsonl"))
+        self.log_dir = os.path.join(save_dir, "lightning_logs", f"version_{version}")
+        self.experiment = _ScalarLog(os.path.join(self.log_dir, "scalars.jsonl") if writer else None)
 
 
 class LightningModule(nn.Module):
@@ -117,14 +123,31 @@ class Trainer:
               ("--log_every_n_steps", int, 50), ("--resume_from_checkpoint", str, None), ("--profiler", str, None)]
 
     def __init__(self, gpus=1, max_epochs=1, default_root_dir=".", limit_train_batches=-1, limit_val_batches=-1,
-                 **_ignored):
+                 resume_from_checkpoint=None, **_ignored):
         self.gpus, self.max_epochs = gpus, max_epochs
         self.limit_train_batches, self.limit_val_batches = limit_train_batches, limit_val_batches
+        self.resume_from_checkpoint = resume_from_checkpoint
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
-        self.logger = _Logger(default_root_dir)
+        if isinstance(gpus, int) and gpus > 1 and self.world_size == 1:
+            import warnings
+            warnings.warn(f"--gpus {gpus} but WORLD_SIZE is 1: this Trainer runs one process per GPU - launch it with "
+                          f"`python -m torch.distributed.run --nproc-per-node {gpus} -m model.optimize ...`; "
+                          f"continuing on ONE GPU")
+        if resume_from_checkpoint and not os.path.isfile(resume_from_checkpoint):
+            raise FileNotFoundError(f"--resume_from_checkpoint {resume_from_checkpoint}: no such file")
+        # rank 0 picks the log version; the others follow it (each picking its own would race on the directory list)
+        version = None
+        if self.world_size > 1:
+            self._setup_distributed()
+            import torch.distributed as dist
+            box = [next_log_version(default_root_dir) if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            version = box[0]
+        self.logger = _Logger(default_root_dir, version, writer=self.rank == 0)
         self.global_step = 0
+        self.start_epoch = 0
 
     @classmethod
     def add_argparse_args(cls, parser: ArgumentParser) -> ArgumentParser:
@@ -141,7 +164,68 @@ class Trainer:
     def _setup_distributed(self):
         import torch.distributed as dist
         if self.world_size > 1 and not dist.is_initialized():
-            dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+            if torch.cuda.is_available():
+                torch.cuda.set_device(self.local_rank)
+                dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(backend="gloo")
+
+    # ---- checkpoints (Lightning's default ModelCheckpoint: lightning_logs/version_N/checkpoints/epoch=E-step=S.ckpt
+    #      every epoch, latest only; the reference relies on it implicitly, model.py:69-72 + optimize.py:30,241) -------
+    def checkpoint_dir(self) -> str:
+        return os.path.join(self.logger.log_dir, "checkpoints")
+
+    def save_checkpoint(self, model, optimizer, schedulers, epoch: int) -> Optional[str]:
+        """Collective (the sharded Adam moments are gathered); rank 0 writes.  Keys follow Lightning's .ckpt layout:
+        `state_dict` (the texture layers - the frozen VGG is reloaded from vgg_gatys_model_path), `optimizer_states`
+        (torch.optim.Adam layout), `lr_schedulers`, `epoch` (the next epoch to run), `global_step`."""
+        opt_state = optimizer.state_dict()
+        if self.rank != 0:
+            return None
+        tex = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if k.startswith("texture.")}
+        ckpt = {"epoch": epoch + 1, "global_step": self.global_step, "state_dict": tex,
+                "optimizer_states": [opt_state], "lr_schedulers": [s.state_dict() for s in schedulers],
+                "hyper_parameters": {k: v for k, v in getattr(model, "hparams", {}).items()
+                                     if isinstance(v, (int, float, str, bool, list, dict, type(None)))},
+                "gram_cache": {k: [g.detach().cpu() for g in v] for k, v in
+                               getattr(getattr(model, "vgg_loss", None), "gram_cache", {}).items()},
+                "stylemesh_b200": {"world_size": self.world_size}}
+        d = self.checkpoint_dir()
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, f"epoch={epoch}-step={self.global_step}.ckpt")
+        tmp = path + ".tmp"
+        torch.save(ckpt, tmp)
+        os.replace(tmp, path)
+        for old in os.listdir(d):
+            if old.endswith(".ckpt") and os.path.join(d, old) != path:
+                os.remove(os.path.join(d, old))
+        return path
+
+    def load_checkpoint(self, path: str, model, optimizer, schedulers) -> None:
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        own = model.state_dict()
+        missing = [k for k in own if k.startswith("texture.") and k not in ckpt["state_dict"]]
+        if missing:
+            raise KeyError(f"{path}: texture entries missing from the checkpoint: {missing}")
+        with torch.no_grad():
+            for k, v in ckpt["state_dict"].items():
+                if k in own and k.startswith("texture."):
+                    if own[k].shape != v.shape:
+                        raise ValueError(f"{path}: {k} is {tuple(v.shape)}, the model has {tuple(own[k].shape)}")
+                    own[k].copy_(v.to(own[k].device))
+        if ckpt.get("optimizer_states"):
+            optimizer.load_state_dict(ckpt["optimizer_states"][0])
+        for s, sd in zip(schedulers, ckpt.get("lr_schedulers", [])):
+            s.load_state_dict(sd)
+        for g in optimizer.param_groups:                   # StepLR keeps the decayed lr in its own state
+            if schedulers and getattr(schedulers[0], "_last_lr", None):
+                g["lr"] = schedulers[0]._last_lr[0]
+        cache = ckpt.get("gram_cache") or {}
+        if cache and hasattr(getattr(model, "vgg_loss", None), "gram_cache"):
+            dev = next(model.parameters()).device
+            model.vgg_loss.gram_cache = {k: [g.to(dev) for g in v] for k, v in cache.items()}
+        self.start_epoch = int(ckpt.get("epoch", 0))
+        self.global_step = int(ckpt.get("global_step", 0))
 
     def _my_batches(self, loader):
         """(batch_idx, batch) of this rank: view sharding, rank r owns views r, r+N, ...  Every rank must take the same
@@ -170,12 +254,25 @@ class Trainer:
         model.trainer, model.logger = self, self.logger
         if hasattr(model, "cache_view_plans"):
             model.cache_view_plans = True      # views repeat (RepeatingSampler): build each view's mask plan once
+        dm_args = getattr(datamodule, "args", None)
+        if getattr(dm_args, "batch_size", 1) != 1:
+            raise ValueError("batch_size must be 1: one view per step and rank (the reference's masked_features breaks "
+                             "for batch_size > 1, content_and_style_losses.py:137); use more GPUs for more views per step")
+        if hasattr(getattr(model, "vgg_loss", None), "cache_content_targets") and \
+                getattr(dm_args, "sampler_mode", None) == "repeat" and getattr(dm_args, "index_repeat", 1) > 1:
+            # VGG(target) is constant per view (cs:294) and the repeat sampler shows every view index_repeat times in a
+            # row (abstract_dataset.py:498-512): compute it on the first visit only
+            model.vgg_loss.cache_content_targets = True
+        if self.rank != 0 and hasattr(model, "save_texture"):
+            model.save_texture = False         # rank 0 exports the (replicated) texture
         (optimizer,), schedulers = model.configure_optimizers()
+        if self.resume_from_checkpoint:
+            self.load_checkpoint(self.resume_from_checkpoint, model, optimizer, schedulers)
         train_loader = datamodule.train_dataloader()
         val_loader = datamodule.val_dataloader()
         from .staging import BatchStager
         stager = BatchStager(device)
-        for epoch in range(self.max_epochs):
+        for epoch in range(self.start_epoch, self.max_epochs):
             model.current_epoch = epoch
             model.on_train_epoch_start()
             model.train()
@@ -196,7 +293,7 @@ class Trainer:
                 stager.release(cur_ticket)
                 self.global_step += 1
             model.on_train_epoch_end()
-            if val_loader is not None:
+            if val_loader is not None and self.rank == 0:      # replicas are identical: rank 0 validates and logs
                 model.on_validation_epoch_start()
                 model.eval()
                 with torch.no_grad():
@@ -208,5 +305,11 @@ class Trainer:
             model.on_epoch_end()
             for s in schedulers:
                 s.step()
+            self.save_checkpoint(model, optimizer, schedulers, epoch)
             self.logger.experiment.flush()
+            if self.world_size > 1:
+                # nobody enters the next epoch's first exchange (a device-side spin-wait with a watchdog) while rank 0
+                # still validates / writes files
+                torch.cuda.synchronize()
+                torch.distributed.barrier()
         return model

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 
 from ... import _abi
 from ... import engine as _eng
+from ...view_cache import ViewLRU
 
 _ALL_CONVS = [("conv1_1", 3, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("conv2_2", 128, 128),
               ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), ("conv3_4", 256, 256),
@@ -124,7 +125,8 @@ def build_loss_plan(level_sizes, pyramid_masks, angle_degrees, angle_threshold, 
     stats = []
     for (H, W), mask in zip(level_sizes, pyramid_masks):
         entry = {"size": (H, W), "layers": {}}
-        m4 = (mask.reshape(1, 1, H, W) > 0).float()       # {0,1}: the engine's row masks select pixels (cs:137 `mask > 0`)
+        raw4 = mask.reshape(1, 1, H, W).float()
+        m4 = (raw4 > 0).float()                            # {0,1}: the engine's row masks select pixels (cs:137 `mask > 0`)
         if need_angle_split:
             passed = F.interpolate(angle_degrees, (H, W), mode="bilinear") < angle_threshold      # cs:161
             m_pass4, m_fail4 = m4 * passed, m4 * (~passed)
@@ -134,6 +136,9 @@ def build_loss_plan(level_sizes, pyramid_masks, angle_degrees, angle_threshold, 
             m = F.interpolate(m4, (h, w), mode="nearest").reshape(-1).contiguous()                 # cs:172
             rec = {"conv": conv, "hw": (h, w), "mask": m}
             stats.append(m.sum())
+            # cs:181: the level factor is the mean of the RAW nearest-resized mask values (differs from the pixel count
+            # only for soft masks, which the public ContentAndStyleLoss.forward accepts)
+            stats.append(F.interpolate(raw4, (h, w), mode="nearest").sum())
             if need_angle_split:
                 rec["mask_pass"] = F.interpolate(m_pass4, (h, w), mode="nearest").reshape(-1).contiguous()
                 rec["mask_fail"] = F.interpolate(m_fail4, (h, w), mode="nearest").reshape(-1).contiguous()
@@ -147,10 +152,11 @@ def build_loss_plan(level_sizes, pyramid_masks, angle_degrees, angle_threshold, 
         for name in layer_names:
             rec = entry["layers"][name]
             rec["n"] = vals[k]; k += 1
+            raw_sum = vals[k]; k += 1
             if need_angle_split:
                 rec["n_pass"] = vals[k]; k += 1
                 rec["n_fail"] = vals[k]; k += 1
-            rec["f_raw"] = rec["n"] / float(rec["hw"][0] * rec["hw"][1])                            # cs:181
+            rec["f_raw"] = raw_sum / float(rec["hw"][0] * rec["hw"][1])                             # cs:181
     for name in layer_names:                                                                        # cs:199-204
         total = sum(e["layers"][name]["f_raw"] for e in plan.levels)
         for e in plan.levels:
@@ -195,7 +201,7 @@ class ContentAndStyleLoss(nn.Module):
         self.style_targets = None
         self.angle_threshold = angle_threshold
         self.cache_content_targets = False             # opt-in: reuse VGG(target) per view index
-        self._content_cache: Dict[object, dict] = {}
+        self._content_cache = ViewLRU(16 << 30)        # VGG(target) features per view, least recently used evicted
 
     # -- style targets (one-off, cs:273-286) ----------------------------------------------------------------
     def set_style_image(self, style_image, num_levels=5):
@@ -226,8 +232,10 @@ class ContentAndStyleLoss(nn.Module):
     def content_targets(self, target_content, level_sizes, cache_key=None):
         """VGG(target)[content layers] at the target's own resolution (cs:294), then bilinear-resized to every
         level's layer size (cs:176) and laid out channels-last for the content kernel."""
-        if self.cache_content_targets and cache_key is not None and cache_key in self._content_cache:
-            return self._content_cache[cache_key]
+        if self.cache_content_targets and cache_key is not None:
+            hit = self._content_cache.get(cache_key)
+            if hit is not None:
+                return hit
         eng = self.vgg.engine()
         out = {}
         if self.content_layers:
@@ -250,16 +258,20 @@ class ContentAndStyleLoss(nn.Module):
                         per_level.append(t[0].permute(1, 2, 0).reshape(h * w, C_).contiguous())
                 out[name] = per_level
         if self.cache_content_targets and cache_key is not None:
-            self._content_cache[cache_key] = out
+            self._content_cache.put(cache_key, out)
         return out
 
     # -- the fused evaluation: losses + d(loss)/d(pred) in one pass ------------------------------------------
     def fused_loss_and_grads(self, preds: Sequence[torch.Tensor], plan: LossPlan, content_tgts: dict,
                              style_scale: float, content_scale: float, loss_accum: torch.Tensor,
-                             want_grads: bool = True, update_gram_cache: bool = True,
-                             gram_cache_offset: int = 0):
+                             want_grads: bool = True, gram_history: Optional[dict] = None,
+                             record_history: Optional[dict] = None):
         """preds[i]: (3,H_i,W_i).  Adds style_scale*style_loss to loss_accum[0] and content_scale*content_loss to
-        loss_accum[1]; returns [d(sum)/d(pred_i)] (already scaled) or None."""
+        loss_accum[1]; returns [d(sum)/d(pred_i)] (already scaled) or None.
+        gram_mode='average' (cs:319-323): every (level, layer) term averages its Gram with the <= 9 most recent cached
+        ones - including those of EARLIER LEVELS OF THIS CALL, the cache is shared across levels - and pushes its own.
+        record_history={} receives {(level, layer): (prev_sum, avg_len)} as used; gram_history=<that dict> replays a
+        call with exactly those histories and leaves the cache alone (the autograd backward)."""
         if self.style_targets is None:
             raise RuntimeError("set_style_image() must be called before the loss is evaluated")
         eng = self.vgg.engine()
@@ -277,10 +289,14 @@ class ContentAndStyleLoss(nn.Module):
                 tgt = self.style_targets[idx]
                 prev_sum, avg_len, gram_out = None, 1.0, None
                 if self.gram_mode == "average":                                                  # cs:319-323
-                    # gram_cache_offset=1 replays a step whose own Gram is already at the head of the cache
-                    prev = self.gram_cache[name][gram_cache_offset:gram_cache_offset + 9]
-                    avg_len = float(len(prev) + 1)
-                    prev_sum = torch.stack(prev).sum(0).contiguous() if prev else None
+                    if gram_history is not None:
+                        prev_sum, avg_len = gram_history[(li, name)]
+                    else:
+                        prev = self.gram_cache[name][:9]
+                        avg_len = float(len(prev) + 1)
+                        prev_sum = torch.stack(prev).sum(0).contiguous() if prev else None
+                        if record_history is not None:
+                            record_history[(li, name)] = (prev_sum, avg_len)
                     gram_out = torch.empty_like(tgt[0][0])
                 if multi:                                                                        # cs:305-338
                     eng.style_term(slot, rec["conv"], rec["mask_pass"], _inv(rec["n_pass"]), tgt[2][0], coef,
@@ -291,11 +307,13 @@ class ContentAndStyleLoss(nn.Module):
                 else:
                     eng.style_term(slot, rec["conv"], rec["mask"], _inv(rec["n"]), tgt[0][0], coef, None, 0.0,
                                    acc_style, prev_sum, avg_len, gram_out)
-                if self.gram_mode == "average" and update_gram_cache:
+                if self.gram_mode == "average" and gram_history is None:
                     self.gram_cache[name] = [gram_out] + self.gram_cache[name][:9]
             for idx, name in enumerate(self.content_layers):                                     # cs:343-348
                 rec = entry["layers"][name]
                 if rec["n"] <= 0:
+                    if rec["f"] != rec["f"]:            # cs:199-204: a zero factor sum makes the reference's term NaN
+                        acc_content += float("nan")
                     continue
                 C_ = _eng.CONV_COUT[rec["conv"]]
                 coef_loss = content_scale * self.content_weights[idx] * rec["f"] / (C_ * rec["n"])
@@ -321,15 +339,18 @@ class ContentAndStyleLoss(nn.Module):
 
 
 class _LossFunction(torch.autograd.Function):
-    """Values in forward; in backward the engine re-seeds the terms with the incoming scalar gradients and runs
-    its own backward (the forward activations are still resident in the per-resolution slots)."""
+    """Values in forward; backward re-evaluates the step with the incoming scalar gradients folded into the term
+    coefficients (the VGG forwards are re-run: another evaluation may have reused the per-resolution slots in
+    between) and returns the engine's own data gradients.  The Gram histories of gram_mode='average' are the ones the
+    forward used (stored on ctx), not a re-slice of the live cache."""
 
     @staticmethod
     def forward(ctx, module: ContentAndStyleLoss, plan, tgts, *preds):
         acc = torch.zeros(2, device=preds[0].device, dtype=torch.float32)
         imgs = [p.detach()[0].contiguous() for p in preds]
-        module.fused_loss_and_grads(imgs, plan, tgts, 1.0, 1.0, acc, want_grads=False)
-        ctx.module, ctx.plan, ctx.tgts = module, plan, tgts
+        history = {}
+        module.fused_loss_and_grads(imgs, plan, tgts, 1.0, 1.0, acc, want_grads=False, record_history=history)
+        ctx.module, ctx.plan, ctx.tgts, ctx.history = module, plan, tgts, history
         ctx.save_for_backward(*imgs)
         return acc[0:1].clone(), acc[1:2].clone()
 
@@ -338,5 +359,5 @@ class _LossFunction(torch.autograd.Function):
         gs, gc = torch.stack([g_style.reshape(-1)[0], g_content.reshape(-1)[0]]).tolist()
         scratch = torch.zeros(2, device=g_style.device, dtype=torch.float32)
         grads = ctx.module.fused_loss_and_grads(list(ctx.saved_tensors), ctx.plan, ctx.tgts, gs, gc, scratch,
-                                                want_grads=True, update_gram_cache=False, gram_cache_offset=1)
+                                                want_grads=True, gram_history=ctx.history)
         return (None, None, None, *[g.unsqueeze(0) for g in grads])

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 from .. import engine as _eng
 from ..lightning_shim import LightningModule
+from ..view_cache import ViewLRU
 from .losses.content_and_style_losses import ContentAndStyleLoss, build_loss_plan
 from .losses.rgb_transform import post
 from .texture.texture import HierarchicalNeuralTexture, NeuralTexture, to_image
@@ -47,6 +48,61 @@ class FusedTextureAdam(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none: bool = True):
         pass            # the Adam kernel leaves the flat gradient buffer zeroed; .grad stays a view of it
+
+    def _full_moments(self):
+        """(exp_avg, exp_avg_sq) of the whole flat buffer.  The fused multi-GPU kernel shards the moments (rank r only
+        ever touches slice r of its buffers, the rest stays 0), so the full state is the sum over ranks - collective."""
+        st = self._pipeline._ensure_fused_state()
+        m, v = st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+        if st.get("peer") and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(m)
+            torch.distributed.all_reduce(v)
+        return m, v
+
+    def state_dict(self):
+        """torch.optim.Adam's layout: state[i] = {step, exp_avg, exp_avg_sq} per texture layer (model.py:391-395), so
+        a checkpoint written here loads into the reference's optimizer and vice versa.  Collective when sharded."""
+        st = self._pipeline._ensure_fused_state()
+        m, v = self._full_moments()
+        mods = self._pipeline._layer_modules()
+        state = {i: {"step": torch.tensor(float(self._steps)),
+                     "exp_avg": m[a:b].view_as(mod.data).detach().cpu().clone(),
+                     "exp_avg_sq": v[a:b].view_as(mod.data).detach().cpu().clone()}
+                 for i, (mod, (a, b)) in enumerate(zip(mods, st["spans"]))}
+        groups = [{k: val for k, val in g.items() if k != "params"} for g in self.param_groups]
+        groups[0]["params"] = list(range(len(mods)))
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        st = self._pipeline._ensure_fused_state()
+        mods = self._pipeline._layer_modules()
+        if len(sd["state"]) not in (0, len(mods)):
+            raise ValueError(f"optimizer state has {len(sd['state'])} entries for {len(mods)} texture layers")
+        sharded = bool(st.get("peer")) and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        steps = 0
+        with torch.no_grad():
+            st["exp_avg"].zero_()
+            st["exp_avg_sq"].zero_()
+            for i, (mod, (a, b)) in enumerate(zip(mods, st["spans"])):
+                ent = sd["state"].get(i, sd["state"].get(str(i)))
+                if ent is None:
+                    continue
+                st["exp_avg"][a:b].copy_(ent["exp_avg"].reshape(-1).to(st["exp_avg"].device, torch.float32))
+                st["exp_avg_sq"][a:b].copy_(ent["exp_avg_sq"].reshape(-1).to(st["exp_avg"].device, torch.float32))
+                steps = max(steps, int(float(ent["step"])))
+            if sharded:            # keep only this rank's slice (same split as dist_adam_kernel: float4 granules)
+                world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+                n4 = st["param"].numel() // 4
+                per = (n4 + world - 1) // world
+                lo, hi = min(rank * per, n4) * 4, min((rank + 1) * per, n4) * 4
+                for buf in (st["exp_avg"], st["exp_avg_sq"]):
+                    buf[:lo].zero_()
+                    buf[hi:].zero_()
+        self._steps = steps
+        for g, new in zip(self.param_groups, sd.get("param_groups", [])):
+            for k, val in new.items():
+                if k != "params":
+                    g[k] = val
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -149,7 +205,7 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
         self._fused: Optional[dict] = None
         self._loss_buf: Optional[torch.Tensor] = None
         self.cache_view_plans = False            # opt-in for resident views (bench `value` leg, repeated views)
-        self._plan_cache: Dict[int, dict] = {}
+        self._plan_cache = ViewLRU(16 << 30)     # per-view masks / hooks / counts, least recently used view evicted
         self._style_ready = False
 
     # ------------------------------------------------------------------------------------------------------
@@ -183,9 +239,11 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
                 flat[a:b].copy_(m.data.detach().reshape(-1).to(torch.float32))
                 m.data.data = flat[a:b].view_as(m.data)
                 m.data.grad = st["grad"][a:b].view_as(m.data)
-        if peer:                                           # replicas start identical (DDP broadcasts rank 0's weights)
-            torch.distributed.broadcast(flat, 0)
-            peer["handles"][0].barrier()
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(flat, 0)                        # replicas start identical (DDP broadcasts rank 0's weights)
+            if peer:
+                peer["handles"][0].barrier()
         self._fused = st
         return st
 
@@ -200,6 +258,7 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
             return None
         if os.environ.get("SMB_DIST_ADAM", "1") == "0" or dist.get_backend() != "nccl" or dist.get_world_size() > 16:
             return None
+        bufs, err = None, None
         try:
             import torch.distributed._symmetric_memory as symm
             bufs, handles = {}, []
@@ -211,11 +270,18 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
                 bufs[name] = t
             bufs["handles"] = handles
             bufs["ptrs"] = {name: [int(p) for p in h.buffer_ptrs] for name, h in zip(("param", "grad", "flags"), handles)}
-            return bufs
         except Exception as e:                             # pragma: no cover - depends on the box
+            bufs, err = None, e
+        # every rank must take the SAME path: a rank in the all_reduce fallback would leave the others spinning in
+        # dist_adam_kernel until its watchdog traps
+        ok = torch.tensor([1 if bufs is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
             import warnings
-            warnings.warn(f"symmetric memory unavailable ({e!r}); falling back to NCCL all_reduce + local Adam")
+            warnings.warn(f"symmetric memory unavailable on at least one rank (here: {err!r}); every rank falls back to "
+                          f"NCCL all_reduce + local Adam")
             return None
+        return bufs
 
     def _layer_tensors(self) -> List[torch.Tensor]:
         return [m.data.detach() for m in self._layer_modules()]
@@ -319,7 +385,7 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
         if vp is None:
             vp = self.build_view_plan(batch)
             if key is not None:
-                self._plan_cache[key] = vp
+                self._plan_cache.put(key, vp)
         keep = vp["keep"]
         layers = self._layer_tensors()
         preds = [_eng.uv_sample_fwd(layers, uvs[i][0]) for i in keep]

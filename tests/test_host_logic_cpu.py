@@ -147,3 +147,62 @@ def test_packed_batch_round_trip():
         assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
     for m in p.meta:
         assert m is None or m[0] % 256 == 0
+
+
+def _loss_modules(tmp_path, preset_name, gram_mode, pyramid_mode):
+    from stylemesh_b200.model.losses.content_and_style_losses import ContentAndStyleLoss
+    from oracle import stylemesh_oracle as orc
+    spec = golden_case_specs()[preset_name]
+    preset, sd, layers, view, style, _ = build_inputs(spec)
+    vgg_path = os.path.join(tmp_path, "vgg.pth")
+    torch.save(sd, vgg_path)
+    mod = ContentAndStyleLoss(vgg_path, style_weights=list(preset["style_weights"]),
+                              angle_threshold=preset["angle_threshold"], style_pyramid_mode=pyramid_mode,
+                              gram_mode=gram_mode)
+    mod.set_style_image(style.unsqueeze(0))
+    loss = orc.StyleContentOracle(vgg_params=sd, style_weights=list(preset["style_weights"]),
+                                  angle_threshold=preset["angle_threshold"], style_pyramid_mode=pyramid_mode,
+                                  gram_mode=gram_mode, as_written=False)
+    loss.set_style_image(style.unsqueeze(0))
+    return mod, loss, view
+
+
+def test_autograd_average_gram_mode_two_levels_uses_the_forward_histories(monkeypatch, tmp_path):
+    """gram_mode='average' with a 2-level pyramid (cs:319-323: the cache is shared across levels, so level 1 averages
+    with level 0's Gram of the SAME call): losses and gradients of three consecutive calls equal the oracle's, also
+    when another forward (a validation pass) runs between a forward and its backward."""
+    fake_engine.install(monkeypatch)
+    mod, loss, view = _loss_modules(tmp_path, "only2D", "average", "single")
+    g = torch.Generator().manual_seed(5)
+    masks = [torch.ones(1, 1, 48, 64), torch.ones(1, 1, 72, 96)]
+    masks[0][..., 50:] = 0
+    masks[1][..., :20] = 0
+    for call in range(3):
+        preds = [torch.rand(1, 3, 48, 64, generator=g) * 100 - 50, torch.rand(1, 3, 72, 96, generator=g) * 100 - 50]
+        p1 = [p.clone().requires_grad_(True) for p in preds]
+        s, c, _ = mod(p1, view.rgb, masks, view.angle_degrees)
+        if call == 1:                                    # an unrelated forward before the backward (validation)
+            with torch.no_grad():
+                saved = {k: list(v) for k, v in mod.gram_cache.items()}
+                mod([p.detach() for p in preds], view.rgb, masks, view.angle_degrees)
+                mod.gram_cache = saved                   # (the oracle does not see this extra call)
+        (1e-4 * s + 70 * c).backward()
+        p2 = [p.clone().requires_grad_(True) for p in preds]
+        os_, oc_ = loss.loss(p2, view.rgb, masks, view.angle_degrees)
+        (1e-4 * os_ + 70 * oc_).backward()
+        assert rel(float(s), float(os_)) < 1e-4 and rel(float(c), float(oc_)) < 1e-4, call
+        for a, b in zip(p1, p2):
+            assert (a.grad - b.grad).norm() <= 1e-4 * b.grad.norm(), call
+
+
+def test_soft_masks_weight_the_levels_like_the_reference(monkeypatch, tmp_path):
+    """cs:181: the level factor is mean(nearest(mask)) of the RAW mask values; `> 0` only selects the pixels (cs:137)."""
+    fake_engine.install(monkeypatch)
+    mod, loss, view = _loss_modules(tmp_path, "only2D", "current", "single")
+    g = torch.Generator().manual_seed(9)
+    masks = [torch.rand(1, 1, 48, 64, generator=g) * 0.5, torch.rand(1, 1, 72, 96, generator=g) * 2.0]
+    masks[0][..., 40:] = 0
+    preds = [torch.rand(1, 3, 48, 64, generator=g) * 100 - 50, torch.rand(1, 3, 72, 96, generator=g) * 100 - 50]
+    s, c, info = mod(preds, view.rgb, masks, view.angle_degrees)
+    os_, oc_ = loss.loss(preds, view.rgb, masks, view.angle_degrees)
+    assert rel(float(s), float(os_)) < 1e-4 and rel(float(c), float(oc_)) < 1e-4
