@@ -7,8 +7,14 @@
 
 The oracle needs 0.6 s (C2) to a few seconds (C3/C4) per step on the box's host cores.  At these sizes the kernels run
 the code paths the 48x64 fixtures never reach: stream-K splits, resident B tiles, 4-buffer TMEM at BN=64, the 146-way
-Gram split, ragged TMA clipping on 341/811/1045-pixel rows.  Bars: loss terms <= 1e-3 relative, dense
-texture gradient <= 1e-2 relative L2, texels after one teacher-forced Adam step by distribution.
+Gram split, ragged TMA clipping on 341/811/1045-pixel rows.
+
+Bars: loss terms <= 1e-3 relative (measured <= 6e-5); texels after one teacher-forced Adam step by distribution (DESIGN
+§5).  The dense texture gradient is judged against the EXACT gradient: the same oracle run in float64.  The gradient
+of a ReLU / max-pool network is discontinuous in the activations, so the reference's own fp32 arithmetic is 0.5 % (C2)
+to 1.4 % (C4, 4096^2 texture: fewer pixels averaged per texel) away from the exact gradient in relative L2
+(profiles/r02_gradient_noise_floor.md).  The CUDA path must be as close to the exact gradient as the fp32 reference
+arithmetic is: err(ours, f64) <= max(1e-2, 1.5 x err(fp32 oracle, f64)).
 
 Unit shapes: the convs / Grams of the benchmark view at the layers where igemm_ph<64> and the r11/r21 Gram kernels run
 (64x480x640, 128x240x320) against torch fp32/fp64 CPU.
