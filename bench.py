@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--sustained-s", type=float, default=5.0,
                     help="length of the sustained leg (same step looped, clocks/power sampled); 0 = skip")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
-    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc1", "pair", "halo", "ph", "simt"])
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "ph", "simt"])
     return ap.parse_args()
 
 

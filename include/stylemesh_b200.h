@@ -29,11 +29,9 @@ extern "C" {
 
 /* implementation selectors for smb_ctx_set_impl */
 #define SMB_IMPL_SIMT 0 /* fp32 CUDA-core cross-check kernels            */
-#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (Gram default; convs: persistent stream-K kernel, second generation) */
-#define SMB_IMPL_TC_V1 2 /* convs only: first-generation tcgen05 kernel, one output tile per CTA             */
-#define SMB_IMPL_TC_HALO 4 /* convs only: 3x3 convs load the activation halo once per K-chunk and reuse it for all 9 taps */
+#define SMB_IMPL_TC 1   /* tcgen05 tensor-core kernels (Gram default; convs: persistent stream-K kernel) */
 #define SMB_IMPL_TC_PH 5 /* convs only (DEFAULT): CTA pair + activation halo + TMA-store epilogue for 3x3 convs, stream-K kernel otherwise */
-#define SMB_IMPL_TC_PAIR 3 /* convs only: cta_group::2 CTA-pair kernel for N % 256 == 0, stream-K kernel otherwise */
+/* (2, 3, 4 were earlier tcgen05 conv generations; retired from the library, see git history) */
 
 typedef struct smb_ctx smb_ctx;
 
@@ -153,7 +151,7 @@ int smb_view_erode3x3(const float* x, int H, int W, float* out, void* stream);
 smb_ctx* smb_ctx_create(void);
 void smb_ctx_destroy(smb_ctx* ctx);
 
-/* conv_impl / gram_impl: SMB_IMPL_SIMT or SMB_IMPL_TC. */
+/* conv_impl: SMB_IMPL_SIMT, SMB_IMPL_TC or SMB_IMPL_TC_PH (default); gram_impl: SMB_IMPL_SIMT or SMB_IMPL_TC. */
 int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl);
 
 /* weights_oihw[i]: HOST fp32 (Cout,Cin,3,3) of conv i in state_dict order conv1_1..conv5_1; bias[i]: HOST (Cout). */

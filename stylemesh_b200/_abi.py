@@ -15,9 +15,6 @@ LIB_PATH = os.path.join(_PKG_DIR, "lib", "libstylemesh_b200.so")
 NUM_VGG_CONVS = 13
 IMPL_SIMT = 0
 IMPL_TC = 1
-IMPL_TC_V1 = 2
-IMPL_TC_PAIR = 3
-IMPL_TC_HALO = 4
 IMPL_TC_PH = 5
 
 # (name, restype, argtypes) — must list every symbol of include/stylemesh_b200.h (checked by tests/test_abi.py)

@@ -225,11 +225,7 @@ static int igemm(int impl, const Act& a, const PackedB& b, const Epilogue& ep, c
   if (impl == IMPL_TC_PH)
     return (b.taps == 9 && (b.N % 64 == 0 || b.N == 16)) ? launch_igemm_ph(a, b, ep, st, ft)
                                                          : launch_igemm_tc2(a, b, ep, st);
-  if (impl == IMPL_TC_HALO)
-    return (b.taps == 9 && b.N % 64 == 0) ? launch_igemm_halo(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
-  if (impl == IMPL_TC_PAIR) return (b.N % 128 == 0) ? launch_igemm_tc3(a, b, ep, st) : launch_igemm_tc2(a, b, ep, st);
   if (impl == IMPL_TC) return launch_igemm_tc2(a, b, ep, st);
-  if (impl == IMPL_TC_V1) return launch_igemm_tc(a, b, ep, st);
   return launch_igemm_simt(a, b, ep, st);
 }
 // masked Gram partials: the tcgen05 kernel masks pixels in shared memory, the SIMT kernel reads a masked copy
@@ -513,10 +509,9 @@ void smb_ctx_destroy(smb_ctx* ctx) { delete ctx; }
 
 int smb_ctx_set_impl(smb_ctx* ctx, int conv_impl, int gram_impl) {
   SMB_REQUIRE(ctx, "null context");
-  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC || conv_impl == IMPL_TC_V1 || conv_impl == IMPL_TC_PAIR ||
-               conv_impl == IMPL_TC_HALO || conv_impl == IMPL_TC_PH) &&
+  SMB_REQUIRE((conv_impl == IMPL_SIMT || conv_impl == IMPL_TC || conv_impl == IMPL_TC_PH) &&
                   (gram_impl == IMPL_SIMT || gram_impl == IMPL_TC),
-              "conv_impl must be SMB_IMPL_SIMT / SMB_IMPL_TC / SMB_IMPL_TC_V1, gram_impl SMB_IMPL_SIMT / SMB_IMPL_TC");
+              "conv_impl must be SMB_IMPL_SIMT / SMB_IMPL_TC / SMB_IMPL_TC_PH, gram_impl SMB_IMPL_SIMT / SMB_IMPL_TC");
   ctx->conv_impl = conv_impl;
   ctx->gram_impl = gram_impl;
   return SMB_OK;
@@ -618,7 +613,7 @@ static int level_forward_impl(smb_ctx* ctx, int slot, const float* image, int la
     ep.out_lo = s.y[0].lo;
     ScopedTimer tm(ctx->timing, CLS_CONV_FIRST, st, 2.0 * 27 * 64 * (double)s.H * s.W);
     int rc;
-    if (ctx->conv_impl != IMPL_SIMT && ctx->conv_impl != IMPL_TC_V1)
+    if (ctx->conv_impl != IMPL_SIMT)
       rc = launch_conv_first_tc(image, s.H, s.W, ctx->conv[0].fwd.hi, ctx->conv[0].fwd.lo, ctx->conv[0].bias, ep, st);
     else
       rc = launch_conv_first_fwd(image, s.H, s.W, ctx->conv[0].w_oihw, ctx->conv[0].bias, kCout[0], ep, st);
@@ -880,7 +875,7 @@ int smb_level_backward(smb_ctx* ctx, int slot, float* d_image, void* stream) {
   }
   {
     ScopedTimer tm(ctx->timing, CLS_FIRST_DGRAD, st, 2.0 * 27 * 64 * (double)s.H * s.W);
-    if (ctx->conv_impl != IMPL_SIMT && ctx->conv_impl != IMPL_TC_V1) {
+    if (ctx->conv_impl != IMPL_SIMT) {
       Epilogue ep;                          // tcgen05 implicit GEMM with N padded 3 -> 16, planar fp32 output
       ep.out_planar3 = d_image;
       rc = igemm(ctx->conv_impl, s.dz[0], ctx->conv[0].dgrad, ep, st);

@@ -99,13 +99,11 @@ struct Epilogue {
   __nv_bfloat16* outm_lo = nullptr;
 };
 
-enum ConvImpl : int { IMPL_SIMT = 0, IMPL_TC = 1, IMPL_TC_V1 = 2, IMPL_TC_PAIR = 3, IMPL_TC_HALO = 4, IMPL_TC_PH = 5 };
+enum ConvImpl : int { IMPL_SIMT = 0, IMPL_TC = 1, IMPL_TC_PH = 5 };   // 2..4: retired tcgen05 generations (git history)
 
 // generic 3x3 (taps==9, pad 1) or 1x1 (taps==1) implicit GEMM: out[p][n] = sum_tap sum_k A[p+off(tap)][k] * B[tap][n][k]
 int launch_igemm_simt(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);
-int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);    // v1: one tile per CTA
 int launch_igemm_tc2(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v2: persistent stream-K
-int launch_igemm_tc3(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);   // v3: v2 on CTA pairs (N % 128 == 0)
 void set_igemm_trace(unsigned long long* buf);   // tc_igemm_v2.cu: per-CTA timeline of the following launches
 // Optional 1x1 term accumulated by igemm_ph into the same tile before the epilogue:
 //   acc[p][n] += rowmask[p] * sum_k f[p][k] * g[n][k]       (Gram backward of the layer that receives the gradient:
@@ -117,7 +115,6 @@ struct FusedTerm {
 };
 int launch_igemm_ph(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st,
                     const FusedTerm* ft = nullptr);    // v5: CTA pair + A halo + TMA-store epilogue (3x3 only)
-int launch_igemm_halo(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st);  // v4: 3x3 only, A halo reused by 9 taps
 
 // first layer (3 -> 64) from the fp32 planar image and its data gradient (64 -> 3)
 int launch_conv_first_fwd(const float* img, int H, int W, const float* w_oihw, const float* bias, int Cout,

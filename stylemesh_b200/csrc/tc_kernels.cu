@@ -1,13 +1,8 @@
 // tcgen05 (5th-gen tensor core) kernels for sm_100a:
 //
-//  igemm_tc_kernel — implicit-GEMM 3x3 / 1x1 convolution on channels-last bf16 hi/lo planes.
-//      D[128 pixels][BN outputs] (fp32, TMEM)  =  sum_tap sum_kchunk  A_tap[128][64] * B_tap[BN][64]^T
-//      executed as three bf16 MMAs per K step (hi*hi + lo*hi + hi*lo): ~2^-16 relative product error,
-//      i.e. fp32-grade parity with the reference's fp32 convs at 1/3 of the bf16 tensor rate.
-//      A tiles are TH x TW pixel patches fetched by 3-D TMA boxes {64 ch, TW, TH} at (x0+dx, y0+dy): the zero
-//      padding of the convolution IS the TMA out-of-bounds fill, so there is no im2col buffer and no halo code.
-//      Used for: VGG conv forward (bias+ReLU epilogue), data-gradient convs (ReLU-mask / addend epilogue),
-//      and the Gram backward  dF = Fm * Bmat  (taps == 1).
+//  (the convolutions live in tc_igemm_v5.cu [pair + halo, the product kernel], tc_igemm_v2.cu [stream-K, 1x1 and odd
+//   shapes] and tc_conv_first.cu; all operands are channels-last bf16 hi/lo planes, three bf16 MMAs per product:
+//   hi*hi + lo*hi + hi*lo, ~2^-16 relative product error at 1/3 of the bf16 tensor rate)
 //
 //  gram_tc_kernel — masked Gram partials  G_s[i][j] = sum_{p in split s} Fm[p][i] Fm[p][j]  with both operands
 //      MN-major straight out of the channels-last planes (TMA boxes {64 ch, 64 pixels}), split over pixel ranges
@@ -28,134 +23,6 @@ constexpr int TC_BK = 64;                       // bf16 elements per K chunk = o
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_SMEM_BUDGET = 196608;          // ring bytes (+ alignment slack + barriers below)
 constexpr int TC_SMEM_EXTRA = 1024 + 256;
-
-struct IGemmTcParams {
-  int H, W, TH, TW, tiles_x, kchunks, taps, N;
-  Epilogue ep;
-};
-
-template <int BN>
-struct IGemmCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = TC_SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static_assert(STAGES >= 2, "need at least a double buffer");
-};
-
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                const IGemmTcParams prm) {
-  using Cfg = IGemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int y0 = (tile / prm.tiles_x) * prm.TH, x0 = (tile % prm.tiles_x) * prm.TW;
-  const int n0 = blockIdx.y * BN;
-  const int num_iters = prm.taps * prm.kchunks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA_hi);
-    tma_prefetch_desc(&tmA_lo);
-    tma_prefetch_desc(&tmB_hi);
-    tma_prefetch_desc(&tmB_lo);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      for (int it = 0; it < num_iters; ++it) {
-        const int stage = it % Cfg::STAGES;
-        const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u, 1);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        const int tap = it / prm.kchunks, kc = it % prm.kchunks;
-        const int dy = (prm.taps == 9) ? tap / 3 - 1 : 0;
-        const int dx = (prm.taps == 9) ? tap % 3 - 1 : 0;
-        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        tma_load_3d(st, &tmA_hi, &full_bar[stage], kc * TC_BK, x0 + dx, y0 + dy);
-        tma_load_3d(st + TC_A_BYTES, &tmA_lo, &full_bar[stage], kc * TC_BK, x0 + dx, y0 + dy);
-        tma_load_3d(st + 2 * TC_A_BYTES, &tmB_hi, &full_bar[stage], kc * TC_BK, n0, tap);
-        tma_load_3d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, &full_bar[stage], kc * TC_BK, n0, tap);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
-      for (int it = 0; it < num_iters; ++it) {
-        const int stage = it % Cfg::STAGES;
-        const uint32_t phase = (uint32_t)(it / Cfg::STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase, 2);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + TC_A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
-        const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // K-major SWIZZLE_128B: 8-row groups 1024 B apart; K advance inside the swizzle row = +32 B
-          const uint64_t dah = make_smem_desc_sw128(a_hi + k * 32, 16, 1024);
-          const uint64_t dal = make_smem_desc_sw128(a_lo + k * 32, 16, 1024);
-          const uint64_t dbh = make_smem_desc_sw128(b_hi + k * 32, 16, 1024);
-          const uint64_t dbl = make_smem_desc_sw128(b_lo + k * 32, 16, 1024);
-          umma_f16(tmem_base, dal, dbh, idesc, (uint32_t)((it | k) != 0));   // small terms first
-          umma_f16(tmem_base, dah, dbl, idesc, 1u);
-          umma_f16(tmem_base, dah, dbh, idesc, 1u);
-        }
-        umma_commit(&empty_bar[stage]);     // frees this smem stage once the MMAs above have read it
-      }
-      umma_commit(tmem_full_bar);           // accumulator complete
-    }
-  } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    mbar_wait(tmem_full_bar, 0, 3);
-    tc_fence_after();
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int yy = y0 + row / prm.TW, xx = x0 + row % prm.TW;
-    const bool valid = (yy < prm.H) && (xx < prm.W);
-    const int64_t p = (int64_t)yy * prm.W + xx;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      if (valid) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_store<32>(prm.ep, p, n0 + c, prm.N, v);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Gram partials (both operands MN-major)
@@ -368,65 +235,6 @@ static void pick_patch(int H, int W, int& TH, int& TW) {
   }
   TH = best_th;
   TW = best_tw;
-}
-
-template <int BN>
-static int launch_igemm_tc_bn(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  using Cfg = IGemmCfg<BN>;
-  IGemmTcParams prm;
-  prm.H = a.H;
-  prm.W = a.W;
-  pick_patch(a.H, a.W, prm.TH, prm.TW);
-  prm.tiles_x = ceil_div(a.W, prm.TW);
-  const int tiles_y = ceil_div(a.H, prm.TH);
-  prm.kchunks = b.K / TC_BK;
-  prm.taps = b.taps;
-  prm.N = b.N;
-  prm.ep = ep;
-
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  {
-    const uint64_t dims[3] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H};
-    const uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2};
-    const uint32_t box[3] = {(uint32_t)TC_BK, (uint32_t)prm.TW, (uint32_t)prm.TH};
-    int rc = make_tmap_bf16(&tmA_hi, a.hi, 3, dims, strides, box);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tmA_lo, a.lo, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)b.K, (uint64_t)b.N, (uint64_t)b.taps};
-    const uint64_t strides[2] = {(uint64_t)b.K * 2, (uint64_t)b.N * b.K * 2};
-    const uint32_t box[3] = {(uint32_t)TC_BK, (uint32_t)BN, 1u};
-    int rc = make_tmap_bf16(&tmB_hi, b.hi, 3, dims, strides, box);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tmB_lo, b.lo, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  const int smem_bytes = Cfg::STAGES * Cfg::STAGE_BYTES + TC_SMEM_EXTRA;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMB_CUDA_CHECK(cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
-  dim3 grid(prm.tiles_x * tiles_y, b.N / BN);
-  SMB_LAUNCH(igemm_tc_kernel<BN>, grid, TC_THREADS, smem_bytes, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, prm);
-  return SMB_OK;
-}
-
-int launch_igemm_tc(const Act& a, const PackedB& b, const Epilogue& ep, cudaStream_t st) {
-  SMB_REQUIRE(b.taps == 9 || b.taps == 1, "igemm_tc: taps must be 1 or 9");
-  SMB_REQUIRE(a.C == b.K && b.K % TC_BK == 0, "igemm_tc: K=%d must equal the activation channels and be a multiple of 64",
-              b.K);
-  SMB_REQUIRE(b.N % 64 == 0, "igemm_tc: N=%d must be a multiple of 64", b.N);
-  if (a.pixels() == 0) return SMB_OK;
-  // widest N tile that divides N keeps the MMA at full rate (M128 x N256 x K16 reads 96 B/clk of smem);
-  // small spatial maps prefer more, narrower tiles so that all 148 SMs get work.
-  const int64_t mtiles = ceil_div64(a.pixels(), 128);
-  if (b.N % 256 == 0 && mtiles * (b.N / 256) >= 148) return launch_igemm_tc_bn<256>(a, b, ep, st);
-  if (b.N % 128 == 0 && mtiles * (b.N / 128) >= 148) return launch_igemm_tc_bn<128>(a, b, ep, st);
-  if (b.N % 128 == 0 && b.N >= 256 && mtiles * (b.N / 64) < 148) return launch_igemm_tc_bn<128>(a, b, ep, st);
-  return launch_igemm_tc_bn<64>(a, b, ep, st);
 }
 
 template <int BN, bool ALIAS>

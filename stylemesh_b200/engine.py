@@ -285,17 +285,11 @@ def _impl_from_env(name: str, default: int) -> int:
         return default
     if v in ("tc", "tcgen05", "1"):
         return _abi.IMPL_TC
-    if v in ("tc1", "tc_v1", "2"):
-        return _abi.IMPL_TC_V1
-    if v in ("pair", "tc_pair", "tc3", "3"):
-        return _abi.IMPL_TC_PAIR
-    if v in ("halo", "tc_halo", "tc4", "4"):
-        return _abi.IMPL_TC_HALO
     if v in ("ph", "tc_ph", "tc5", "5"):
         return _abi.IMPL_TC_PH
     if v in ("simt", "0"):
         return _abi.IMPL_SIMT
-    raise ValueError(f"{name}={v!r}: expected 'tc' or 'simt'")
+    raise ValueError(f"{name}={v!r}: expected 'ph' (pair + halo tcgen05 convs), 'tc' (stream-K tcgen05) or 'simt'")
 
 
 class VGGEngine:

@@ -266,6 +266,7 @@ class Trainer:
         if self.rank != 0 and hasattr(model, "save_texture"):
             model.save_texture = False         # rank 0 exports the (replicated) texture
         (optimizer,), schedulers = model.configure_optimizers()
+        self.optimizers, self.lr_schedulers = [optimizer], list(schedulers)
         if self.resume_from_checkpoint:
             self.load_checkpoint(self.resume_from_checkpoint, model, optimizer, schedulers)
         train_loader = datamodule.train_dataloader()

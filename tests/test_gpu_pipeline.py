@@ -57,8 +57,8 @@ def assert_texels(got, want, what=""):
 
 
 def make_pipeline(spec, tmp_path, impl):
-    # "tc" = the product default (pair + halo conv kernel); SMB_TEST_TC_VARIANT=tc|pair|halo|tc1 re-runs these cases on
-    # another tcgen05 conv kernel generation
+    # "tc" = the product default (pair + halo conv kernel); SMB_TEST_TC_VARIANT=tc re-runs these cases on the stream-K
+    # tcgen05 conv kernel
     os.environ["SMB_CONV_IMPL"] = os.environ.get("SMB_TEST_TC_VARIANT", "ph") if impl == "tc" else impl
     os.environ["SMB_GRAM_IMPL"] = impl
     from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline

@@ -6,8 +6,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc"), pytest.param(2, id="tc1"), pytest.param(3, id="pair"),
-         pytest.param(4, id="halo"), pytest.param(5, id="ph")]
+IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc"), pytest.param(5, id="ph")]
 GRAM_IMPLS = [pytest.param(0, id="simt"), pytest.param(1, id="tc")]
 
 

@@ -206,3 +206,54 @@ def test_soft_masks_weight_the_levels_like_the_reference(monkeypatch, tmp_path):
     s, c, info = mod(preds, view.rgb, masks, view.angle_degrees)
     os_, oc_ = loss.loss(preds, view.rgb, masks, view.angle_degrees)
     assert rel(float(s), float(os_)) < 1e-4 and rel(float(c), float(oc_)) < 1e-4
+
+
+def test_checkpoint_round_trip_restores_texels_moments_step_and_lr(monkeypatch, tmp_path):
+    """Trainer.save_checkpoint / load_checkpoint (Lightning's implicit ModelCheckpoint + --resume_from_checkpoint):
+    texture layers, Adam moments + step in torch.optim.Adam's layout, StepLR state, epoch, global_step."""
+    fake_engine.install(monkeypatch)
+    from stylemesh_b200.lightning_shim import Trainer
+    from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline
+    spec = golden_case_specs()["only2D"]
+    preset, sd, layers, view, style, hierarchical = build_inputs(spec)
+    vgg_path = os.path.join(tmp_path, "vgg.pth")
+    torch.save(sd, vgg_path)
+
+    def make():
+        return TextureOptimizationStyleTransferPipeline(
+            64, 64, hierarchical_texture=True, hierarchical_layers=len(layers), random_texture_init=True,
+            style_image=style.clone(), style_weights=list(preset["style_weights"]), vgg_gatys_model_path=vgg_path,
+            use_angle_weight=False, use_depth_scaling=False, learning_rate=1.0, decay_gamma=0.5, decay_step_size=1,
+            loss_weights=dict(preset["loss_weights"]), save_texture=False)
+
+    a = make()
+    (opt,), (sched,) = a.configure_optimizers()
+    for i in range(3):
+        a.training_step(view.as_batch(), i)["loss"].backward()
+        opt.step()
+    sched.step()
+    tr = Trainer(default_root_dir=str(tmp_path))
+    tr.global_step = 3
+    path = tr.save_checkpoint(a, opt, [sched], epoch=0)
+    assert os.path.basename(path) == "epoch=0-step=3.ckpt"
+    ck = torch.load(path, weights_only=False)
+    ref_adam = torch.optim.Adam([torch.nn.Parameter(t.clone()) for t in layers], lr=1.0)
+    ref_adam.load_state_dict(ck["optimizer_states"][0])               # the reference's optimizer accepts our state
+    assert int(ref_adam.state_dict()["state"][0]["step"]) == 3
+
+    b = make()
+    (opt_b,), (sched_b,) = b.configure_optimizers()
+    tr2 = Trainer(default_root_dir=str(tmp_path), resume_from_checkpoint=path)
+    tr2.load_checkpoint(path, b, opt_b, [sched_b])
+    assert tr2.start_epoch == 1 and tr2.global_step == 3 and opt_b._steps == 3
+    assert abs(opt_b.param_groups[0]["lr"] - 0.5) < 1e-12
+    for ma, mb in zip(a.texture.layers, b.texture.layers):
+        assert torch.equal(ma.data, mb.data)
+    sa, sb = a._ensure_fused_state(), b._ensure_fused_state()
+    assert torch.equal(sa["exp_avg"], sb["exp_avg"]) and torch.equal(sa["exp_avg_sq"], sb["exp_avg_sq"])
+    # the next step of both is identical
+    for m, o in ((a, opt), (b, opt_b)):
+        m.training_step(view.as_batch(), 3)["loss"].backward()
+        o.step()
+    for ma, mb in zip(a.texture.layers, b.texture.layers):
+        assert torch.equal(ma.data, mb.data)
