@@ -12,6 +12,7 @@
 #include "../../include/stylemesh_b200.h"
 #include "smb_common.cuh"
 #include "smb_kernels.h"
+#include "tc_common.cuh"
 
 namespace smb {
 
@@ -28,6 +29,13 @@ const char* get_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace tc {
+TmapCache& tmap_cache() {
+  static TmapCache c;
+  return c;
+}
+}  // namespace tc
 
 // programmatic dependent launch (smb_common.cuh) is on unless SMB_PDL=0
 bool pdl_enabled() {

@@ -5,6 +5,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include "smb_common.cuh"
 
 namespace smb {
@@ -174,9 +177,56 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// bf16 tensor, `rank` dims (dim 0 innermost/contiguous), SWIZZLE_128B, zero fill out of bounds.
+// `rank` dims (dim 0 innermost/contiguous), SWIZZLE_128B, zero fill out of bounds.
+//
+// Encoded maps are memoised: a step issues ~30 conv launches per pyramid level with 6-10 tensor maps each, and every
+// one of them describes a tensor that lives as long as its resolution slot (activation planes, packed weights) - the
+// same (base, shape, box) comes back every step.  cuTensorMapEncodeTiled costs a few microseconds; the 4-level presets
+// spent most of their host time per step in it.  A map depends only on the key below, so a hit is exact even if the
+// memory behind `base` was freed and re-allocated in between.
+struct TmapKey {
+  uint64_t v[10];
+  bool operator==(const TmapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 0x100000001b3ull;
+      h ^= h >> 29;
+    }
+    return (size_t)h;
+  }
+};
+struct TmapCache {
+  std::mutex mu;
+  std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> map;
+  long long hits = 0, misses = 0;
+};
+TmapCache& tmap_cache();      // engine.cu (one instance per library)
+
 inline int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes /* rank-1 entries, for dims 1.. */, const uint32_t* box) {
+  TmapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = ((uint64_t)dtype << 8) | (uint64_t)rank;
+  for (int i = 0; i < rank && i < 3; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[5 + i] = box[i];
+    if (i > 0) key.v[7 + i] = strides_bytes[i - 1];
+  }
+  TmapCache& cache = tmap_cache();
+  if (rank <= 3) {
+    std::lock_guard<std::mutex> lock(cache.mu);
+    auto it = cache.map.find(key);
+    if (it != cache.map.end()) {
+      *out = it->second;
+      ++cache.hits;
+      return SMB_OK;
+    }
+  }
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -199,6 +249,12 @@ inline int make_tmap_typed(CUtensorMap* out, CUtensorMapDataType dtype, const vo
               rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
     return SMB_ERR_CUDA;
+  }
+  if (rank <= 3) {
+    std::lock_guard<std::mutex> lock(cache.mu);
+    if (cache.map.size() >= 65536) cache.map.clear();      // bounded: a long-lived process with many resolutions
+    cache.map.emplace(key, *out);
+    ++cache.misses;
   }
   return SMB_OK;
 }
