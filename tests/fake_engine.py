@@ -25,10 +25,11 @@ def uv_scatter_bwd(grad_layers, grid, grad_out, hook0=None, hook1=None):
     if hook1 is not None:
         g = g * hook1.reshape(1, *g.shape[1:])
     for gl in grad_layers:
-        z = torch.zeros_like(gl).requires_grad_(True)
-        y = F.grid_sample(z.unsqueeze(0), grid.unsqueeze(0), mode="bilinear", padding_mode="border",
-                          align_corners=True)[0]
-        (dz,) = torch.autograd.grad(y, z, g)
+        with torch.enable_grad():            # the product calls us from inside an autograd.Function's backward
+            z = torch.zeros_like(gl).requires_grad_(True)
+            y = F.grid_sample(z.unsqueeze(0), grid.unsqueeze(0), mode="bilinear", padding_mode="border",
+                              align_corners=True)[0]
+            (dz,) = torch.autograd.grad(y, z, g)
         gl += dz
 
 
