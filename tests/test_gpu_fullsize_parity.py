@@ -185,14 +185,25 @@ def test_second_visit_uses_the_caches_and_still_matches_oracle(tmp_path):
         n_plans, n_tgts = len(mdl._plan_cache), len(mdl.vgg_loss._content_cache)
         out = mdl.training_step(dev[vi], visit)
         hits.append((len(mdl._plan_cache) == n_plans, len(mdl.vgg_loss._content_cache) == n_tgts))
-        buf = mdl._loss_buf.cpu()
+        buf = mdl._loss_buf.cpu().clone()
         for k, i in (("style", 0), ("content", 1), ("tex_reg", 2), ("total", 3)):
             assert rel(float(buf[i]), want_loss[k]) < LOSS_TOL, (visit, k, float(buf[i]), want_loss[k])
         lam = float(mdl.loss_weights["tex_reg"])
-        for l, (g, gg) in enumerate(zip([g.cpu() for g in mdl._grad_tensors()], want_grads)):
+        grads_cached = [g.clone() for g in mdl._grad_tensors()]
+        for l, (g, gg) in enumerate(zip([g.cpu() for g in grads_cached], want_grads)):
             x = pipe.layers[l].detach().clamp(orc.CLAMP_LO, orc.CLAMP_HI)
             data_want = gg - lam * mdl.tex_reg_weights[l] * 2.0 * x / x.numel()
-            assert (g - data_want).norm() <= GRAD_TOL * data_want.norm() + 1e-12, (visit, l)
+            # vs the fp32 oracle: bounded by the oracle's own gradient noise floor (profiles/r02_gradient_noise_floor.md)
+            assert (g - data_want).norm() <= 3e-2 * data_want.norm() + 1e-12, (visit, l)
+        # the same step recomputed with both caches OFF: everything up to the scatter is deterministic, the scatter
+        # adds with float atomics -> equal to rounding
+        mdl._fused["grad"].zero_()
+        mdl.cache_view_plans, mdl.vgg_loss.cache_content_targets = False, False
+        buf2 = mdl.fused_view_step(dev[vi]).cpu().clone()
+        mdl.cache_view_plans, mdl.vgg_loss.cache_content_targets = True, True
+        assert torch.allclose(buf, buf2, rtol=1e-5, atol=0), (visit, buf, buf2)
+        for l, (a, b) in enumerate(zip(grads_cached, mdl._grad_tensors())):
+            assert (a - b).norm() <= 1e-5 * b.norm() + 1e-20, (visit, l, float((a - b).norm() / b.norm()))
         out["loss"].backward()
         opt.step()
     assert hits == [(False, False), (False, False), (True, True), (True, True), (True, True)], hits

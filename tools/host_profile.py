@@ -26,14 +26,23 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 for i in range(a.steps):
     bench.one_step(mdl, opt, views[i % len(views)], i)
-host = (time.perf_counter() - t0) / a.steps
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / a.steps
-pr = cProfile.Profile()
-pr.enable()
+# host cost of ENQUEUEING a step into an empty launch queue (in a free-running loop the queue fills up and every
+# launch blocks on the GPU, so the loop's host time equals the device time)
+host = 0.0
 for i in range(a.steps):
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     bench.one_step(mdl, opt, views[i % len(views)], i)
-pr.disable()
+    host += time.perf_counter() - t1
+host /= a.steps
+pr = cProfile.Profile()
+for i in range(a.steps):
+    torch.cuda.synchronize()
+    pr.enable()
+    bench.one_step(mdl, opt, views[i % len(views)], i)
+    pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
