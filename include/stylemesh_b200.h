@@ -143,6 +143,25 @@ int smb_view_angle_degrees(const float* cos_angle, int64_t n, float* degrees, vo
 /* erode of model/model.py:204-208: out = x where the zero-padded 3x3 box mean of x is exactly 1, else 0. */
 int smb_view_erode3x3(const float* x, int H, int W, float* out, void* stream);
 
+/* Mask pyramid of a view (model/model.py:204-254 + content_and_style_losses.py:161,172-185) in 1 + L launches.
+ * smb_view_level_masks: all L pyramid levels at the rgb resolution (H x W): level_mask[l] = erode(((rounded == l) |
+ *   (other == l)) & mask), level_weight[l] = erode((rounded == l) & mask) * w + erode((other == l) & mask) * (1 - w);
+ *   mask: H*W bytes (0 / non-zero), rounded / other: int64, outputs [L][H*W] fp32. */
+int smb_view_level_masks(const unsigned char* mask, const int64_t* rounded, const int64_t* other,
+                         const float* interp_w, int H, int W, int num_levels, float* level_mask, float* level_weight,
+                         void* stream);
+/* smb_view_level_plan: one pyramid level of size H x W from maps at the rgb resolution Hr x Wr.
+ *   src_mask (values > 0 select; nearest-resampled), src_weight -> hook1 [H*W] (nearest; both may be NULL),
+ *   angle_guidance -> hook0 [H*W] (bilinear; both may be NULL); for each of the num_layers (<= 8) VGG layers of size
+ *   lh[k] x lw[k]: the nearest-downsampled {0,1} row mask and, with split != 0, the masks of the pixels whose
+ *   bilinear angle_degrees is below / not below `threshold`, written back to back into layer_masks
+ *   ([all | pass | fail] per layer, or [all] without the split).
+ *   counts: 1 + 3*num_layers uint32 (device): selected level pixels, then (n, n_pass, n_fail) per layer. */
+int smb_view_level_plan(const float* src_mask, const float* src_weight, const float* angle_guidance,
+                        const float* angle_degrees, float threshold, int Hr, int Wr, int H, int W, float* hook0,
+                        float* hook1, int num_layers, const int* lh, const int* lw, float* layer_masks, int split,
+                        unsigned int* counts, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
  * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the

@@ -259,6 +259,14 @@ static int igemm_timed(smb_ctx* ctx, int cls, const Act& a, const PackedB& b, co
   return igemm(ctx->conv_impl, a, b, ep, st, ft);
 }
 
+static bool pool_side_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMB_PH_POOL_SIDE");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
 // SMB_PH_FUSE=0 keeps every Gram backward as its own launch (fp32 pending gradient + addend read in the conv epilogue)
 static bool fuse_enabled() {
   static const bool on = [] {
@@ -497,6 +505,25 @@ int smb_view_erode3x3(const float* x, int H, int W, float* out, void* stream) {
   return launch_view_erode3x3(x, H, W, out, (cudaStream_t)stream);
 }
 
+int smb_view_level_masks(const unsigned char* mask, const int64_t* rounded, const int64_t* other, const float* interp_w,
+                         int H, int W, int num_levels, float* level_mask, float* level_weight, void* stream) {
+  SMB_REQUIRE(mask && rounded && other && interp_w && level_mask && level_weight && H >= 0 && W >= 0 && num_levels >= 0,
+              "view_level_masks: bad argument");
+  return launch_view_level_masks(mask, reinterpret_cast<const long long*>(rounded),
+                                 reinterpret_cast<const long long*>(other), interp_w, H, W, num_levels, level_mask,
+                                 level_weight, (cudaStream_t)stream);
+}
+
+int smb_view_level_plan(const float* src_mask, const float* src_weight, const float* angle_guidance,
+                        const float* angle_degrees, float threshold, int Hr, int Wr, int H, int W, float* hook0,
+                        float* hook1, int num_layers, const int* lh, const int* lw, float* layer_masks, int split,
+                        unsigned int* counts, void* stream) {
+  SMB_REQUIRE(Hr > 0 && Wr > 0 && H > 0 && W > 0, "view_level_plan: empty map");
+  SMB_REQUIRE(num_layers == 0 || (lh && lw), "view_level_plan: null layer sizes");
+  return launch_view_level_plan(src_mask, src_weight, angle_guidance, angle_degrees, threshold, Hr, Wr, H, W, hook0,
+                                hook1, num_layers, lh, lw, layer_masks, split, counts, (cudaStream_t)stream);
+}
+
 // ---- context --------------------------------------------------------------------------------------------------
 smb_ctx* smb_ctx_create(void) {
   int dev = -1;
@@ -639,17 +666,24 @@ static int level_forward_impl(smb_ctx* ctx, int slot, const float* image, int la
       }
       x = s.pooled[i];
     }
-    const bool pool_out = inference && ctx->conv_impl == IMPL_TC_PH && i < last_conv && kPoolBefore[i + 1] &&
-                          !((keep_mask >> i) & 1) && kCout[i] % 64 == 0;
+    const bool feeds_pool = ctx->conv_impl == IMPL_TC_PH && i < last_conv && kPoolBefore[i + 1] && kCout[i] % 64 == 0;
+    const bool pool_out = inference && feeds_pool && !((keep_mask >> i) & 1);
+    // a materialised layer that feeds a pool writes the pooled planes as a side output of its epilogue (no pool launch,
+    // no second read of the full-resolution features); SMB_PH_POOL_SIDE=0 keeps the separate pool kernel
+    const bool pool_side = feeds_pool && !pool_out && pool_side_enabled();
     Epilogue ep;
     ep.bias = ctx->conv[i].bias;
     ep.relu = 1;
     ep.out_hi = pool_out ? s.pooled[i + 1].hi : s.y[i].hi;
     ep.out_lo = pool_out ? s.pooled[i + 1].lo : s.y[i].lo;
     ep.pool2x2 = pool_out ? 1 : 0;
+    if (pool_side) {
+      ep.pool_hi = s.pooled[i + 1].hi;
+      ep.pool_lo = s.pooled[i + 1].lo;
+    }
     int rc = igemm_timed(ctx, CLS_IGEMM_FWD, x, ctx->conv[i].fwd, ep, st);
     if (rc) return rc;
-    pooled_ready = pool_out;
+    pooled_ready = pool_out || pool_side;
     if (!pool_out) s.valid |= 1u << i;
   }
   s.last_done = last_conv;

@@ -61,6 +61,14 @@ int launch_view_depth_levels(const double* depth, int64_t n, const double* level
 int launch_view_rgb_pre(const unsigned char* hwc, int H, int W, float* chw, cudaStream_t st);
 int launch_view_angle_degrees(const float* c, int64_t n, float* deg, cudaStream_t st);
 int launch_view_erode3x3(const float* x, int H, int W, float* out, cudaStream_t st);
+#define SMB_MAX_PLAN_LAYERS 8
+int launch_view_level_masks(const unsigned char* mask, const long long* rounded, const long long* other,
+                            const float* interp_w, int H, int W, int L, float* level_mask, float* level_weight,
+                            cudaStream_t st);
+int launch_view_level_plan(const float* src_mask, const float* src_weight, const float* angle_guidance,
+                           const float* angle_degrees, float threshold, int Hr, int Wr, int H, int W, float* hook0,
+                           float* hook1, int num_layers, const int* lh, const int* lw, float* layer_masks, int split,
+                           unsigned int* counts, cudaStream_t st);
 
 // ---- VGG side -----------------------------------------------------------------------------------------------
 // Activation planes (see smb_common.cuh): channels-last bf16 hi/lo pair.
@@ -90,6 +98,8 @@ struct Epilogue {
   const __nv_bfloat16* sign_hi = nullptr; // [P][N] (hi plane of the forward activation: ReLU backward mask)
   int relu = 0;
   int pool2x2 = 0;                        // igemm_ph only: out_hi/out_lo are the (H/2, W/2) planes of maxpool2x2(v)
+  __nv_bfloat16* pool_hi = nullptr;       // igemm_ph only, next to out_hi/out_lo: side output maxpool2x2(v) as (H/2, W/2)
+  __nv_bfloat16* pool_lo = nullptr;       //   planes (training forward of a layer that feeds a pool: no pool launch)
   __nv_bfloat16* out_hi = nullptr;
   __nv_bfloat16* out_lo = nullptr;
   float* out_f32 = nullptr;

@@ -787,6 +787,13 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             continue;
           }
           const uint32_t ch0 = (uint32_t)((c & 63) >> 3);
+          // side output for a layer that feeds MaxPool2d(2,2): the 2x2 window partners of patch pixel (py, px) =
+          // lane (py % 4) * 8 + px of quarter py / 4 are lanes ^1 and ^8; lanes with both bits clear own the window and
+          // store its maximum straight to the pooled planes (a quarter of the pixels, 64 contiguous bytes per plane)
+          const bool pool_side = prm.ep.pool_hi != nullptr;
+          const int pY = yy >> 1, pX = xx >> 1;
+          const bool pool_store = pool_side && (lane & 9) == 0 && pY < (prm.H >> 1) && pX < (prm.W >> 1);
+          const int64_t poff = ((int64_t)pY * (prm.W >> 1) + pX) * prm.N + n0 + c;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 h, l;
@@ -797,6 +804,24 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const uint32_t a = rbase + (((ch0 + (uint32_t)j) ^ sw) << 4);
             i5_sts128(a, h);
             i5_sts128(a + I5_OUT_PLANE, l);
+            if (pool_side) {                     // (warp-uniform branch: the shuffles need all 32 lanes)
+              float m[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = v[8 * j + e];
+                t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                m[e] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+              }
+              if (pool_store) {
+                uint4 ph, pl;
+                split2_pack(m[0], m[1], ph.x, pl.x);
+                split2_pack(m[2], m[3], ph.y, pl.y);
+                split2_pack(m[4], m[5], ph.z, pl.z);
+                split2_pack(m[6], m[7], ph.w, pl.w);
+                *reinterpret_cast<uint4*>(prm.ep.pool_hi + poff + 8 * j) = ph;
+                *reinterpret_cast<uint4*>(prm.ep.pool_lo + poff + 8 * j) = pl;
+              }
+            }
           }
           {                                      // 64-channel group complete: one tensor store per plane
             fence_proxy_async_smem();
@@ -917,6 +942,8 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     else if (ep.out_f32 && !ep.out_hi) prm.tma_out = 2;
   }
   SMB_REQUIRE(!ep.pool2x2 || prm.tma_out == 3, "igemm_ph: the pooled epilogue needs hi/lo outputs only and N %% 64 == 0");
+  SMB_REQUIRE(!ep.pool_hi || (prm.tma_out == 1 && ep.pool_lo),
+              "igemm_ph: the pooled side output needs hi/lo outputs through the staged epilogue and N %% 64 == 0");
   static int no_tma_out = -1;
   if (no_tma_out < 0) {
     const char* e = getenv("SMB_PH_DIRECT_STORES");     // experiment knob: 1 = per-thread global stores as in igemm_tc2

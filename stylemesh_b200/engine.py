@@ -276,6 +276,69 @@ def view_erode3x3(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def view_level_masks(mask: torch.Tensor, rounded: torch.Tensor, other: torch.Tensor, interp_w: torch.Tensor,
+                     num_levels: int):
+    """model/model.py:210-239 for ALL pyramid levels at the rgb resolution in one launch.
+    mask (H,W) bool/uint8, rounded / other (H,W) int64, interp_w (H,W) f32 ->
+    (level_mask (L,H,W) f32 = erode(((rounded == l) | (other == l)) & mask),
+     level_weight (L,H,W) f32 = erode((rounded == l) & mask) * w + erode((other == l) & mask) * (1 - w))."""
+    lib = _abi.load()
+    m = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+    m = _require_cuda(m.contiguous(), torch.uint8, "mask")
+    r = _require_cuda(rounded.contiguous(), torch.int64, "rounded_depth_level")
+    o = _require_cuda(other.contiguous(), torch.int64, "other_depth_level")
+    w = _require_cuda(interp_w.contiguous(), torch.float32, "depth_level_interpolation_weight")
+    H, W = m.shape[-2], m.shape[-1]
+    if not (m.numel() == r.numel() == o.numel() == w.numel() == H * W):
+        raise ValueError("view_level_masks takes (H, W) maps of one view")
+    lm = torch.empty((num_levels, H, W), device=m.device, dtype=torch.float32)
+    lw = torch.empty((num_levels, H, W), device=m.device, dtype=torch.float32)
+    _abi.check(lib.smb_view_level_masks(_abi.ptr(m), _abi.ptr(r), _abi.ptr(o), _abi.ptr(w), H, W, int(num_levels),
+                                        _abi.ptr(lm), _abi.ptr(lw), _abi.current_stream()), "smb_view_level_masks")
+    return lm, lw
+
+
+def view_level_plan(src_mask: torch.Tensor, src_weight: Optional[torch.Tensor], angle_guidance: Optional[torch.Tensor],
+                    angle_degrees: Optional[torch.Tensor], threshold: float, level_hw, layer_hw, counts: torch.Tensor):
+    """One pyramid level in one launch (model.py:199,219,238,253-254 + cs:161,172-185): returns
+    {"hook0": (H*W,) | None, "hook1": (H*W,) | None, "layers": [{"mask", "mask_pass"?, "mask_fail"?}, ...]} and fills
+    `counts` (uint32/int32 device tensor of 1 + 3*len(layer_hw)): selected level pixels, then (n, n_pass, n_fail) per
+    layer.  src_* are (Hr, Wr) maps at the rgb resolution; angle_degrees=None skips the pass / fail split."""
+    lib = _abi.load()
+    sm = _require_cuda(src_mask, torch.float32, "src_mask")
+    Hr, Wr = sm.shape[-2], sm.shape[-1]
+    H, W = int(level_hw[0]), int(level_hw[1])
+    for t, name in ((src_weight, "src_weight"), (angle_guidance, "angle_guidance"), (angle_degrees, "angle_degrees")):
+        if t is not None:
+            _require_cuda(t, torch.float32, name)
+            if t.numel() != Hr * Wr:
+                raise ValueError(f"{name} must have the rgb resolution {Hr}x{Wr}")
+    split = angle_degrees is not None
+    nl = len(layer_hw)
+    if counts.numel() < 1 + 3 * nl or counts.element_size() != 4 or not counts.is_cuda:
+        raise ValueError("counts must be a CUDA 32-bit integer tensor of 1 + 3 * len(layer_hw) entries")
+    hook0 = torch.empty(H * W, device=sm.device, dtype=torch.float32) if angle_guidance is not None else None
+    hook1 = torch.empty(H * W, device=sm.device, dtype=torch.float32) if src_weight is not None else None
+    per = 3 if split else 1
+    sizes = [int(h) * int(w) for h, w in layer_hw]
+    buf = torch.empty(per * sum(sizes), device=sm.device, dtype=torch.float32)
+    _abi.check(lib.smb_view_level_plan(_abi.ptr(sm), _abi.ptr(src_weight), _abi.ptr(angle_guidance),
+                                       _abi.ptr(angle_degrees), float(threshold), Hr, Wr, H, W, _abi.ptr(hook0),
+                                       _abi.ptr(hook1), nl, _abi.int_array([h for h, _ in layer_hw]),
+                                       _abi.int_array([w for _, w in layer_hw]), _abi.ptr(buf), int(split),
+                                       _abi.ptr(counts), _abi.current_stream()), "smb_view_level_plan")
+    layers, off = [], 0
+    for n in sizes:
+        rec = {"mask": buf[off:off + n]}
+        off += n
+        if split:
+            rec["mask_pass"] = buf[off:off + n]
+            rec["mask_fail"] = buf[off + n:off + 2 * n]
+            off += 2 * n
+        layers.append(rec)
+    return {"hook0": hook0, "hook1": hook1, "layers": layers}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # VGG / loss engine
 # ---------------------------------------------------------------------------------------------------------------

@@ -164,6 +164,32 @@ def build_loss_plan(level_sizes, pyramid_masks, angle_degrees, angle_threshold, 
     return plan
 
 
+def loss_plan_from_counts(level_sizes, per_level, counts_per_level, layer_names, need_angle_split):
+    """LossPlan from the mask-pyramid kernel's outputs (engine.view_level_plan): per_level[i]["layers"][k] holds the
+    row masks of layer_names[k], counts_per_level[i] = [alive, n_0, n_pass_0, n_fail_0, n_1, ...] (host ints).
+    Same fields and the same factor normalisation as build_loss_plan (cs:181,199-204); the level masks are binary, so
+    the raw mean of cs:181 equals n / (h * w)."""
+    plan = LossPlan()
+    for (H, W), lv, cnt in zip(level_sizes, per_level, counts_per_level):
+        entry = {"size": (H, W), "layers": {}}
+        for k, name in enumerate(layer_names):
+            conv = _eng.layer_index(name)
+            h, w = layer_hw(conv, H, W)
+            rec = {"conv": conv, "hw": (h, w), "mask": lv["layers"][k]["mask"], "n": float(cnt[1 + 3 * k])}
+            if need_angle_split:
+                rec["mask_pass"] = lv["layers"][k]["mask_pass"]
+                rec["mask_fail"] = lv["layers"][k]["mask_fail"]
+                rec["n_pass"], rec["n_fail"] = float(cnt[2 + 3 * k]), float(cnt[3 + 3 * k])
+            rec["f_raw"] = rec["n"] / float(h * w)
+            entry["layers"][name] = rec
+        plan.levels.append(entry)
+    for name in layer_names:
+        total = sum(e["layers"][name]["f_raw"] for e in plan.levels)
+        for e in plan.levels:
+            e["layers"][name]["f"] = (e["layers"][name]["f_raw"] / total) if total > 0 else float("nan")
+    return plan
+
+
 def _inv(n: float) -> float:
     return 1.0 / n if n > 0 else 0.0
 

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from .. import engine as _eng
 from ..lightning_shim import LightningModule
 from ..view_cache import ViewLRU
-from .losses.content_and_style_losses import ContentAndStyleLoss, build_loss_plan
+from .losses.content_and_style_losses import ContentAndStyleLoss, layer_hw, loss_plan_from_counts
 from .losses.rgb_transform import post
 from .texture.texture import HierarchicalNeuralTexture, NeuralTexture, to_image
 
@@ -336,31 +336,42 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
         return _eng.view_erode3x3(x.to(torch.float32).contiguous())
 
     def build_view_plan(self, batch) -> dict:
+        """Everything about a view's masks that the step needs (model.py:188-257 + cs:146-217): per kept pyramid level
+        the angle hook (bilinear), the depth-interpolation hook (nearest of the eroded level weights), the per-layer
+        row masks with the angle pass / fail split and their pixel counts.  1 + L launches of the mask-pyramid kernels
+        (csrc/mask_plan_kernels.cu) and ONE host read-back of the counts; cached per view by fused_view_step."""
         (rgb, _, _, _, _, rounded, other, interp_w, _, uvs, mask, angle_guidance, angle_degrees) = batch
         sizes = [(int(u.shape[1]), int(u.shape[2])) for u in uvs]
-        mask_f = mask.unsqueeze(1).float()
-        masks, dweights = [], [None] * len(sizes)
-        if self.use_depth_scaling:                                                       # model.py:210-251
-            for i, size in enumerate(sizes):
-                m = (((rounded == i) + (other == i)).float()) * mask_f
-                masks.append((F.interpolate(self._erode(m), size, mode="nearest") > 0).float())
-                m1 = self._erode((rounded == i) * mask_f) * interp_w
-                m2 = self._erode((other == i) * mask_f) * (1 - interp_w)
-                dweights[i] = F.interpolate(m1 + m2, size, mode="nearest").reshape(-1).contiguous()
-        else:                                                                            # model.py:253-254
-            masks = [torch.zeros(1, 1, *s, device=mask_f.device) for s in sizes]
-            masks[-1] = (F.interpolate(mask_f, sizes[-1], mode="nearest") > 0).float()
-        alive = torch.stack([m.sum() for m in masks]).tolist()                           # model.py:256-257
-        keep = [i for i, s in enumerate(alive) if s > 0]
-        hooks0 = {}
-        if self.use_angle_weight:                                                        # model.py:195-202
-            for i in keep:
-                hooks0[i] = F.interpolate(angle_guidance, sizes[i], mode="bilinear").reshape(-1).contiguous()
+        L = len(sizes)
+        Hr, Wr = int(mask.shape[-2]), int(mask.shape[-1])
         style_on = self.loss_weights.get("style", 0.0) != 0.0
         layer_names = (self.vgg_loss.style_layers if style_on else []) + self.vgg_loss.content_layers
-        plan = build_loss_plan([sizes[i] for i in keep], [masks[i] for i in keep], angle_degrees,
-                               self.vgg_loss.angle_threshold, layer_names,
-                               self.vgg_loss.style_pyramid_mode == "multi" and style_on)
+        split = self.vgg_loss.style_pyramid_mode == "multi" and style_on
+        convs = [_eng.layer_index(n) for n in layer_names]
+        if self.use_depth_scaling:                                                       # model.py:210-251
+            lvl_mask, lvl_weight = _eng.view_level_masks(mask.reshape(Hr, Wr), rounded.reshape(Hr, Wr),
+                                                         other.reshape(Hr, Wr), interp_w.reshape(Hr, Wr).float(), L)
+            todo = list(range(L))
+        else:                                                                            # model.py:253-254
+            lvl_mask, lvl_weight = mask.reshape(1, Hr, Wr).float().contiguous(), None
+            todo = [L - 1]                               # every other level has an all-zero mask and is dropped (:256)
+        guidance = angle_guidance.reshape(Hr, Wr).float().contiguous() if self.use_angle_weight else None
+        degrees = angle_degrees.reshape(Hr, Wr).float().contiguous() if split else None
+        stride = 1 + 3 * len(layer_names)
+        counts = torch.zeros(max(len(todo), 1) * stride, device=mask.device, dtype=torch.int32)
+        per_level = {}
+        for j, i in enumerate(todo):
+            per_level[i] = _eng.view_level_plan(
+                lvl_mask[i if self.use_depth_scaling else 0], lvl_weight[i] if lvl_weight is not None else None, guidance,
+                degrees, float(self.vgg_loss.angle_threshold), sizes[i], [layer_hw(c, *sizes[i]) for c in convs],
+                counts[j * stride:(j + 1) * stride])
+        host = counts.tolist()                                                           # the one host sync of the plan
+        cnt = {i: host[j * stride:(j + 1) * stride] for j, i in enumerate(todo)}
+        keep = [i for i in todo if cnt[i][0] > 0]                                        # model.py:256-257
+        plan = loss_plan_from_counts([sizes[i] for i in keep], [per_level[i] for i in keep], [cnt[i] for i in keep],
+                                     layer_names, split)
+        hooks0 = {i: per_level[i]["hook0"] for i in keep if self.use_angle_weight}       # model.py:195-202
+        dweights = [per_level[i]["hook1"] if i in per_level else None for i in range(L)]  # model.py:247-251
         return {"keep": keep, "sizes": sizes, "hook0": hooks0, "hook1": dweights, "plan": plan,
                 "layer_names": layer_names}
 

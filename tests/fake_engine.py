@@ -113,6 +113,45 @@ def view_erode3x3(x):
     return x * (m == 1)
 
 
+def view_level_masks(mask, rounded, other, interp_w, num_levels):
+    """model/model.py:210-239 with the reference's own torch ops (the emulation doubles as the K5 kernels' reference)."""
+    H, W = mask.shape[-2], mask.shape[-1]
+    mask_f = mask.reshape(1, 1, H, W).float()
+    r, o, w = rounded.reshape(1, 1, H, W), other.reshape(1, 1, H, W), interp_w.reshape(1, 1, H, W).float()
+    lm, lw = [], []
+    for i in range(num_levels):
+        lm.append(orc.erode((((r == i) + (o == i)).float()) * mask_f)[0, 0])
+        m1 = orc.erode((r == i) * mask_f) * w
+        m2 = orc.erode((o == i) * mask_f) * (1 - w)
+        lw.append((m1 + m2)[0, 0])
+    return torch.stack(lm), torch.stack(lw)
+
+
+def view_level_plan(src_mask, src_weight, angle_guidance, angle_degrees, threshold, level_hw, layer_hw, counts):
+    """model.py:199,219,238,253-254 + cs:161,172-185 with torch ops; same outputs as engine.view_level_plan."""
+    Hr, Wr = src_mask.shape[-2], src_mask.shape[-1]
+    H, W = level_hw
+    up = lambda t, mode: F.interpolate(t.reshape(1, 1, Hr, Wr).float(), (H, W), mode=mode)
+    M = (up(src_mask, "nearest") > 0).float()
+    out = {"hook0": up(angle_guidance, "bilinear").reshape(-1).contiguous() if angle_guidance is not None else None,
+           "hook1": up(src_weight, "nearest").reshape(-1).contiguous() if src_weight is not None else None, "layers": []}
+    vals = [int(M.sum())]
+    split = angle_degrees is not None
+    if split:
+        passed = up(angle_degrees, "bilinear") < threshold
+    for (h, w) in layer_hw:
+        rec = {"mask": F.interpolate(M, (h, w), mode="nearest").reshape(-1).contiguous()}
+        n = [int(rec["mask"].sum()), 0, 0]
+        if split:
+            rec["mask_pass"] = F.interpolate(M * passed, (h, w), mode="nearest").reshape(-1).contiguous()
+            rec["mask_fail"] = F.interpolate(M * (~passed), (h, w), mode="nearest").reshape(-1).contiguous()
+            n[1], n[2] = int(rec["mask_pass"].sum()), int(rec["mask_fail"].sum())
+        out["layers"].append(rec)
+        vals += n
+    counts[:len(vals)] = torch.tensor(vals, dtype=counts.dtype)
+    return out
+
+
 def unit_gram(impl, f, rowmask, inv_n):
     fl = f.reshape(f.shape[0], -1)
     if rowmask is not None:
@@ -217,6 +256,7 @@ def install(monkeypatch):
     from stylemesh_b200.model import model as pm
     for name in ["uv_sample_fwd", "uv_scatter_bwd", "adam_step", "texreg_value", "adam_step_segments",
                  "texreg_value_segments", "unit_gram", "VGGEngine", "view_uv_to_grid", "view_gather2d",
-                 "view_resize_linear", "view_depth_levels", "view_rgb_pre", "view_angle_degrees", "view_erode3x3"]:
+                 "view_resize_linear", "view_depth_levels", "view_rgb_pre", "view_angle_degrees", "view_erode3x3",
+                 "view_level_masks", "view_level_plan"]:
         monkeypatch.setattr(engine, name, globals()[name])
     monkeypatch.setattr(engine, "require_cuda_device", lambda dev: None)
