@@ -162,6 +162,17 @@ int smb_view_level_plan(const float* src_mask, const float* src_weight, const fl
                         float* hook1, int num_layers, const int* lh, const int* lw, float* layer_masks, int split,
                         unsigned int* counts, void* stream);
 
+/* Texture export / headless preview.
+ * smb_texture_post_rgb8: post() (model/losses/rgb_transform.py:14-21) + ToPILImage quantisation
+ *   (model/texture/texture.py:9-19): pre()-space BGR fp32 (3,H,W) -> RGB uint8 (H,W,3), device to device.
+ * smb_mip_downsample2x: next mip level ((3, max(H/2,1), max(W/2,1)) fp32) by a 2x2 box filter.
+ * smb_mip_preview: the styled view of model/optimize.py:181-208 without OpenGL: trilinear lookup of the (u, v[, lod])
+ *   map (H,W,uv_channels; u = v = 0 marks pixels without geometry) into the mip chain, post(), RGB uint8 (H,W,3). */
+int smb_texture_post_rgb8(const float* bgr_chw, int H, int W, unsigned char* rgb_hwc, void* stream);
+int smb_mip_downsample2x(const float* src_chw, int H, int W, float* dst_chw, void* stream);
+int smb_mip_preview(const float* const* mips, const int* mip_w, const int* mip_h, int num_mips, const float* uv,
+                    int uv_channels, int H, int W, float lod_bias, unsigned char* rgb_hwc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
  * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the

@@ -524,6 +524,23 @@ int smb_view_level_plan(const float* src_mask, const float* src_weight, const fl
                                 hook1, num_layers, lh, lw, layer_masks, split, counts, (cudaStream_t)stream);
 }
 
+int smb_texture_post_rgb8(const float* bgr_chw, int H, int W, unsigned char* rgb_hwc, void* stream) {
+  SMB_REQUIRE(bgr_chw && rgb_hwc && H >= 0 && W >= 0, "texture_post_rgb8: bad argument");
+  return launch_texture_post_rgb8(bgr_chw, H, W, rgb_hwc, (cudaStream_t)stream);
+}
+
+int smb_mip_downsample2x(const float* src_chw, int H, int W, float* dst_chw, void* stream) {
+  SMB_REQUIRE(src_chw && dst_chw && H > 0 && W > 0, "mip_downsample2x: bad argument");
+  return launch_mip_downsample2x(src_chw, H, W, dst_chw, (cudaStream_t)stream);
+}
+
+int smb_mip_preview(const float* const* mips, const int* mip_w, const int* mip_h, int num_mips, const float* uv,
+                    int uv_channels, int H, int W, float lod_bias, unsigned char* rgb_hwc, void* stream) {
+  SMB_REQUIRE(mips && mip_w && mip_h && uv && rgb_hwc && H >= 0 && W >= 0, "mip_preview: bad argument");
+  return launch_mip_preview(mips, mip_w, mip_h, num_mips, uv, uv_channels, H, W, lod_bias, rgb_hwc,
+                            (cudaStream_t)stream);
+}
+
 // ---- context --------------------------------------------------------------------------------------------------
 smb_ctx* smb_ctx_create(void) {
   int dev = -1;

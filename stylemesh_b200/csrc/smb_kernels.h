@@ -61,6 +61,11 @@ int launch_view_depth_levels(const double* depth, int64_t n, const double* level
 int launch_view_rgb_pre(const unsigned char* hwc, int H, int W, float* chw, cudaStream_t st);
 int launch_view_angle_degrees(const float* c, int64_t n, float* deg, cudaStream_t st);
 int launch_view_erode3x3(const float* x, int H, int W, float* out, cudaStream_t st);
+#define SMB_MAX_MIP_LEVELS 16
+int launch_texture_post_rgb8(const float* bgr_chw, int H, int W, unsigned char* rgb_hwc, cudaStream_t st);
+int launch_mip_downsample2x(const float* src, int Hs, int Ws, float* dst, cudaStream_t st);
+int launch_mip_preview(const float* const* mips, const int* mW, const int* mH, int num_mips, const float* uv,
+                       int uv_channels, int H, int W, float lod_bias, unsigned char* rgb_hwc, cudaStream_t st);
 #define SMB_MAX_PLAN_LAYERS 8
 int launch_view_level_masks(const unsigned char* mask, const long long* rounded, const long long* other,
                             const float* interp_w, int H, int W, int L, float* level_mask, float* level_weight,

@@ -123,6 +123,7 @@ class ViewStoreDataModule(LightningDataModule):
             raise ValueError(f"--scene is required with --dataset {a.dataset} (the reference's random scene search "
                              f"over min/max_images is not reproduced)")
         scene = self._open_scene(a)
+        self.scene = scene                                  # file lists (the preview step re-reads the raw UV + LOD maps)
         n = len(scene)
         if not ((a.min_images == -1 or n >= a.min_images) and (a.max_images == -1 or n <= a.max_images)):
             raise ValueError(f"scene {a.scene} has {n} images, outside [--min_images {a.min_images}, "

@@ -35,4 +35,6 @@ def post():
         y = x.detach().to("cpu") * (1.0 / 255.0)
         y = y + _mean(y)
         return y[[2, 1, 0]].clamp(0, 1)
-    return _Transform(inv)
+    t = _Transform(inv)
+    t.is_reference_post = True      # lets the texture modules run the export chain on the device (stylemesh_b200.export)
+    return t

@@ -5,8 +5,9 @@ In scope: flag parsing, model construction, the training loop (lightning_shim.Tr
 `--dataset scannet|matterport`: one scene / house region in the reference's directory layout, prepared once on the
 device and kept resident (stylemesh_b200/data, SURVEY §8f.2).  `--dataset synthetic` generates seeded views in memory;
 other datasets plug in through `register_datamodule`.
-Out of scope (SURVEY §2 #6,#9-#11): the multi-scene dataset classes and the post-run OpenGL mip-map render / video /
-LPIPS evaluation.
+`--renderer_mipmap cuda` replaces the post-run OpenGL mip-map render of the styled views (optimize.py:181-208) by a
+trilinear lookup of the views' own (u, v, LOD) maps on the device (stylemesh_b200.export.MipPreview).
+Out of scope (SURVEY §2 #6,#9-#11): the multi-scene dataset classes, the video and the LPIPS / reprojection evaluation.
 """
 from __future__ import annotations
 
@@ -125,7 +126,36 @@ def main(args):
         log_images_nth=args.log_images_nth, save_texture=args.save_texture, texture_dir=log_dir)
 
     trainer.fit(model, dm)
+    if args.renderer_mipmap == "cuda" and trainer.rank == 0:       # optimize.py:167-208 without the OpenGL renderer
+        render_previews(model, dm, join(log_dir, "preview"), max_views=args.preview_views,
+                        lod_bias=args.preview_lod_bias)
     return model
+
+
+def render_previews(model, dm, out_dir: str, max_views: int = 16, lod_bias: float = 0.0):
+    """The reference's post-run step renders the scene with the final texture through its OpenGL renderer
+    (GL_LINEAR_MIPMAP_LINEAR, model/optimize.py:181-208).  Headless equivalent: every view's UV map already stores
+    (u, v, mip LOD) per pixel (render_uv/shader/uvmap.frag:8-13), so the styled view is a trilinear lookup into the
+    texture's mip chain (stylemesh_b200.export.MipPreview) - validation views first, `max_views` at most."""
+    import numpy as np
+    from .. import export
+    os.makedirs(out_dir, exist_ok=True)
+    mips = export.MipPreview(model.texture)
+    dev = mips.levels[0].device
+    order = list(getattr(dm, "val_indices", [])) + list(getattr(dm, "train_indices", []))
+    written = []
+    for i in order[:max(0, int(max_views))]:
+        scene = getattr(dm, "scene", None)
+        if scene is not None:                                        # the renderer's (H, W, 3) [u, v, lod] of the finest level
+            uv = torch.from_numpy(np.ascontiguousarray(np.load(scene.uv_levels[-1][i]), dtype=np.float32)).to(dev)
+        else:                                                        # in-memory views: grids in [-1, 1], no LOD channel
+            view = dm._views[i] if hasattr(dm, "_views") else dm.store[i]
+            grid = view.uvs[-1][0] if hasattr(view, "uvs") else view[9][-1][0]
+            uv = export.grid_to_uv(grid.to(dev))
+        path = join(out_dir, f"{i:05d}.jpg")
+        export.save_rgb8(mips.render(uv, lod_bias), path)
+        written.append(path)
+    return written
 
 
 def build_parser() -> ArgumentParser:
@@ -174,7 +204,11 @@ def build_parser() -> ArgumentParser:
     parser.add_argument('--min_pyramid_height', default=32, type=int)
     parser.add_argument('--style_pyramid_mode', default='single', choices=ContentAndStyleLoss.style_pyramid_modes)
     parser.add_argument('--gram_mode', default='current', choices=ContentAndStyleLoss.gram_modes)
-    parser.add_argument('--renderer_mipmap', default=None, type=str)
+    parser.add_argument('--renderer_mipmap', default=None, type=str,
+                        help="the reference passes the path of its OpenGL renderer here; 'cuda' renders the styled "
+                             "views headlessly from the views' own (u, v, LOD) maps after training")
+    parser.add_argument('--preview_views', default=16, type=int)
+    parser.add_argument('--preview_lod_bias', default=0.0, type=float)
     return parser
 
 

@@ -20,6 +20,18 @@ from ... import engine as _eng
 from .utils import from_grid_range
 
 
+def _save_texture_image(module, path, normalize_transform):
+    """texture.py:59-65 / :123-127.  With the reference's post() transform on a CUDA texture the whole chain
+    get_image -> post() -> ToPILImage runs on the device (stylemesh_b200.export.texture_rgb8: same bytes, and only
+    H*W*3 bytes cross PCIe); any other transform takes the reference's host path."""
+    img = module.get_image()
+    if getattr(normalize_transform, "is_reference_post", False) and img.is_cuda:
+        from ... import export as _export
+        _export.save_rgb8(_export.texture_rgb8(module), path)
+        return
+    to_image(img, normalize_transform=normalize_transform).save(path)
+
+
 def to_image(texture, startIndex=0, padChannels=True, normalize_transform=from_grid_range):
     """texture.py:9-19 — first three channels (zero padded) -> PIL image."""
     from torchvision.transforms import ToPILImage
@@ -82,7 +94,7 @@ class NeuralTexture(nn.Module):
         return self.data
 
     def save_image(self, dir, prefix="", normalize_transform=from_grid_range):
-        to_image(self.get_image(), normalize_transform=normalize_transform).save(join(dir, f"{prefix}texture.jpg"))
+        _save_texture_image(self, join(dir, f"{prefix}texture.jpg"), normalize_transform)
 
     def save_layers(self, dir, prefix="", normalize_transform=from_grid_range):
         self.save_image(dir, prefix, normalize_transform)
@@ -136,7 +148,7 @@ class HierarchicalNeuralTexture(nn.Module):
             return self.forward(uv_id)[0, 0:3, :, :]
 
     def save_image(self, dir, prefix="", normalize_transform=from_grid_range):
-        to_image(self.get_image(), normalize_transform=normalize_transform).save(join(dir, f"{prefix}texture.jpg"))
+        _save_texture_image(self, join(dir, f"{prefix}texture.jpg"), normalize_transform)
 
     def save_layers(self, dir, prefix="", normalize_transform=from_grid_range):
         for i, l in enumerate(self.layers):

@@ -22,7 +22,8 @@ def test_cli_runs_and_loss_decreases(family, tmp_path):
             "--style_image_path", "synthetic:96:80", "--default_root_dir", str(tmp_path), "--random_texture_init"]
     if family == "only2D":
         argv += ["--style_pyramid_mode", "single", "--gram_mode", "current", "--angle_threshold", "3000",
-                 "--pyramid_levels", "1", "--no_depth_scaling", "--no_angle_weight"]
+                 "--pyramid_levels", "1", "--no_depth_scaling", "--no_angle_weight", "--renderer_mipmap", "cuda",
+                 "--preview_views", "2"]
     else:
         argv += ["--style_pyramid_mode", "multi", "--gram_mode", "current", "--angle_threshold", "30",
                  "--pyramid_levels", "3"]
@@ -35,6 +36,13 @@ def test_cli_runs_and_loss_decreases(family, tmp_path):
     assert len(tot) == 3 * 3 * 4                      # 3 epochs x 3 train views x index_repeat 4
     assert tot[-1] < 0.9 * tot[0], (tot[0], tot[-1])
     assert any(r["tag"] == "Batch/Loss/val/total" for r in rows)
+    previews = glob.glob(os.path.join(logs[0], "preview", "*.jpg"))
+    assert len(previews) == (2 if family == "only2D" else 0)      # headless styled views (--renderer_mipmap cuda)
+    if previews:
+        from PIL import Image
+        import numpy as np
+        img = np.asarray(Image.open(previews[0]))
+        assert img.shape == (96, 128, 3) and img.std() > 1.0
 
 
 def _argv(tmp, epochs, extra=()):

@@ -160,3 +160,94 @@ def test_segmented_adam_and_texreg_equal_the_per_layer_kernels():
     for a, n in zip(begin, sizes):                         # padding stayed exactly zero
         assert float(p1[a + n:a + (n + 63) // 64 * 64].abs().max() if (n % 64) else 0.0) == 0.0
     assert abs(float(acc1) - float(acc2)) <= 1e-5 * abs(float(acc2))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# texture export and headless preview
+# ---------------------------------------------------------------------------------------------------------------
+def _reference_texture_bytes(layers):
+    """texture.py:110-121 get_image + rgb_transform.py:14-21 post() + texture.py:9-19 ToPILImage, with the reference's
+    torch ops on the CPU."""
+    import torch.nn.functional as F
+    from oracle import stylemesh_oracle as orc
+    C, H, W = layers[0].shape
+    w_range = torch.arange(0, W, dtype=torch.float) / (W - 1.0) * 2.0 - 1.0
+    h_range = torch.arange(0, H, dtype=torch.float) / (H - 1.0) * 2.0 - 1.0
+    v, u = torch.meshgrid(h_range, w_range, indexing="ij")
+    img = orc.texture_sample([l.clone() for l in layers], torch.stack([u, v], 2).unsqueeze(0))[0, 0:3]
+    x = img.clone().mul_(1.0 / 255)
+    mean = torch.tensor([-0.40760392, -0.45795686, -0.48501961]).view(3, 1, 1)
+    x = (x - mean) / 1.0
+    x = x[torch.LongTensor([2, 1, 0])].clamp(0, 1)
+    return x.mul(255).byte().permute(1, 2, 0).contiguous()
+
+
+@pytest.mark.parametrize("size,layers", [(256, 4), (100, 3), (64, 1)])
+def test_texture_export_bytes_match_the_reference_chain(size, layers, tmp_path):
+    from stylemesh_b200 import export, synthetic as syn
+    from stylemesh_b200.model.losses.rgb_transform import post
+    from stylemesh_b200.model.texture.texture import HierarchicalNeuralTexture, NeuralTexture
+    g = torch.Generator().manual_seed(size)
+    ls = [(torch.rand(3, size // 2 ** i, size // 2 ** i, generator=g) * 300 - 140) / (i + 1) for i in range(layers)]
+    if layers == 1:
+        tex = NeuralTexture.from_tensor(ls[0].clone()).cuda()
+        want_layers = [ls[0].clamp(-123.68, 151.061)] if False else ls       # NeuralTexture.get_image(): raw data
+        want = None
+    else:
+        tex = HierarchicalNeuralTexture.from_tensor([l.clone() for l in ls]).cuda()
+    got = export.texture_rgb8(tex).cpu()
+    if layers == 1:                        # texture.py:56-57: the single-layer image is the Parameter itself
+        x = ls[0].clone().mul_(1.0 / 255)
+        x = (x - torch.tensor([-0.40760392, -0.45795686, -0.48501961]).view(3, 1, 1)) / 1.0
+        want = x[torch.LongTensor([2, 1, 0])].clamp(0, 1).mul(255).byte().permute(1, 2, 0).contiguous()
+    else:
+        want = _reference_texture_bytes(ls)
+    assert got.shape == want.shape and got.dtype == torch.uint8
+    diff = (got.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) <= 2e-3, (int(diff.max()), float((diff > 0).float().mean()))
+    # the module's save_image(..., post()) takes the device path and writes the same picture
+    tex.save_image(str(tmp_path), "t_", normalize_transform=post())
+    from PIL import Image
+    import numpy as np
+    jpg = np.asarray(Image.open(str(tmp_path / "t_texture.jpg")).convert("RGB")).astype(int)
+    assert jpg.shape == tuple(want.shape) and np.abs(jpg - want.numpy().astype(int)).mean() < 12     # JPEG coding noise
+
+
+def test_mip_preview_is_gl_trilinear_of_the_box_filtered_chain():
+    """stylemesh_b200.export.MipPreview against torch: mip level l = avg_pool2d^l, GL_LINEAR + CLAMP_TO_EDGE at texel
+    centres = grid_sample(align_corners=False, padding_mode='border'), blended by frac(lod); (0, 0) pixels black."""
+    import torch.nn.functional as F
+    from stylemesh_b200 import export
+    from stylemesh_b200.model.texture.texture import HierarchicalNeuralTexture
+    g = torch.Generator().manual_seed(3)
+    ls = [torch.rand(3, 128 // 2 ** i, 128 // 2 ** i, generator=g) * 200 - 100 for i in range(3)]
+    tex = HierarchicalNeuralTexture.from_tensor([l.clone() for l in ls]).cuda()
+    mips = export.MipPreview(tex)
+    assert [tuple(m.shape[1:]) for m in mips.levels] == [(128 >> i, 128 >> i) for i in range(8)]
+    base = mips.levels[0].cpu()
+    chain = [base]
+    while chain[-1].shape[1] > 1:
+        chain.append(F.avg_pool2d(chain[-1].unsqueeze(0), 2)[0])
+    for a, b in zip(mips.levels, chain):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-4)
+    H, W = 37, 53
+    uv = torch.rand(H, W, 3, generator=g)
+    uv[..., 2] = uv[..., 2] * 5.5 - 0.5                       # LOD in [-0.5, 5]: clamped below, blended above
+    uv[:4, :, :2] = 0.0                                       # no geometry
+    got = mips.render(uv.cuda()).cpu()
+    grid = (uv[..., :2] * 2 - 1).unsqueeze(0)
+    lod = uv[..., 2].clamp(0, len(chain) - 1)
+    l0 = lod.floor().long()
+    l1 = (l0 + 1).clamp(max=len(chain) - 1)
+    t = (lod - l0.float())
+    samples = torch.stack([F.grid_sample(c.unsqueeze(0), grid, mode="bilinear", padding_mode="border",
+                                         align_corners=False)[0] for c in chain])          # (levels, 3, H, W)
+    idx0 = l0.view(1, 1, H, W).expand(1, 3, H, W)
+    idx1 = l1.view(1, 1, H, W).expand(1, 3, H, W)
+    val = samples.gather(0, idx0)[0] * (1 - t) + samples.gather(0, idx1)[0] * t
+    x = val * (1.0 / 255) + torch.tensor([0.40760392, 0.45795686, 0.48501961]).view(3, 1, 1)
+    want = (x[[2, 1, 0]].clamp(0, 1) * 255).byte().permute(1, 2, 0)
+    want[:4] = 0
+    diff = (got.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.02
+    assert int(got[:4].max()) == 0
