@@ -19,6 +19,7 @@ import torch.nn.functional as F
 from .. import engine as _eng
 from ..lightning_shim import LightningModule
 from ..view_cache import ViewLRU
+from .. import nvtx
 from .losses.content_and_style_losses import ContentAndStyleLoss, layer_hw, loss_plan_from_counts
 from .losses.rgb_transform import post
 from .texture.texture import HierarchicalNeuralTexture, NeuralTexture, to_image
@@ -106,6 +107,10 @@ class FusedTextureAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        with nvtx.range("optimizer"):
+            return self._step()
+
+    def _step(self):
         pl = self._pipeline
         st = pl._ensure_fused_state()
         self._steps += 1
@@ -399,7 +404,8 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
                 self._plan_cache.put(key, vp)
         keep = vp["keep"]
         layers = self._layer_tensors()
-        preds = [_eng.uv_sample_fwd(layers, uvs[i][0]) for i in keep]
+        with nvtx.range("sample"):
+            preds = [_eng.uv_sample_fwd(layers, uvs[i][0]) for i in keep]
         w_style = float(self.loss_weights.get("style", 0.0))
         w_content = float(self.loss_weights.get("content", 0.0))
         loss = self.vgg_loss
@@ -408,20 +414,25 @@ class TextureOptimizationStyleTransferPipeline(LightningModule):
             loss.style_layers = []                       # 0 * style_loss: skip the work (and VGG beyond r42)
             loss.layers = loss.content_layers
         try:
-            tgts = loss.content_targets(rgb, [vp["sizes"][i] for i in keep], cache_key=key)
-            grads = loss.fused_loss_and_grads(preds, vp["plan"], tgts, w_style, w_content, buf, want_grads=want_grads)
+            with nvtx.range("content_targets"):
+                tgts = loss.content_targets(rgb, [vp["sizes"][i] for i in keep], cache_key=key)
+            with nvtx.range("vgg_loss"):
+                grads = loss.fused_loss_and_grads(preds, vp["plan"], tgts, w_style, w_content, buf,
+                                                  want_grads=want_grads)
         finally:
             loss.style_layers = saved_style_layers
             loss.layers = saved_style_layers + loss.content_layers
         if want_grads:
-            gl = self._grad_tensors()
-            for j, i in enumerate(keep):
-                _eng.uv_scatter_bwd(gl, uvs[i][0], grads[j], vp["hook0"].get(i), vp["hook1"][i])
+            with nvtx.range("scatter"):
+                gl = self._grad_tensors()
+                for j, i in enumerate(keep):
+                    _eng.uv_scatter_bwd(gl, uvs[i][0], grads[j], vp["hook0"].get(i), vp["hook1"][i])
         mods = self._layer_modules()                                                     # model.py:264-267
         reg = [self._reg_weight(l) / m.data.numel() for l, m in enumerate(mods)]
         if any(c > 0 for c in reg):
-            st = self._ensure_fused_state()
-            _eng.texreg_value_segments(st["param"], [a for a, _ in st["spans"]], reg, buf[2:3])
+            with nvtx.range("regulariser"):
+                st = self._ensure_fused_state()
+                _eng.texreg_value_segments(st["param"], [a for a, _ in st["spans"]], reg, buf[2:3])
         torch.sum(buf[0:3], dim=0, keepdim=True, out=buf[3:4])                           # model.py:270
         return buf
 
