@@ -45,7 +45,7 @@ def _load_reference_lightning_module():
     return mod
 
 
-@pytest.mark.parametrize("case", ["only2D", "with_angle", "with_angle_and_depth", "content_only"])
+@pytest.mark.parametrize("case", ["only2D", "with_angle", "with_angle_and_depth", "content_only", "dip"])
 def test_unmodified_reference_lightning_module_on_our_modules(case, monkeypatch, tmp_path):
     fake_engine.install(monkeypatch)
     ref = _load_reference_lightning_module()
@@ -81,6 +81,8 @@ def test_unmodified_reference_lightning_module_on_our_modules(case, monkeypatch,
         assert (p.grad - gg).norm() <= 1e-4 * gg.norm() + 1e-12, (case, l)
 
     # ---- teacher-forced trajectory with the reference's own Adam ----
+    if case == "dip":
+        mdl.vgg_loss.gram_cache = {k: [] for k in mdl.vgg_loss.style_layers}      # as make_golden.py: restart the average
     (opt,), _ = mdl.configure_optimizers()
     for i in range(spec["steps"]):
         prev = gold["states"][i - 1] if i > 0 else None
