@@ -79,6 +79,7 @@ struct IGemm5Params {
   int resident;               // 1: one K-chunk, one N tile -> the 9 B tiles are loaded once and stay in stages 0..8
   int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
+  int halo_split;             // 1: the activation halo is requested as three 6-row boxes per plane (SMB_PH_HALO_SPLIT)
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do,
                               // 3: only maxpool2x2 of the hi/lo planes is stored (inference-only forward into a pool)
   unsigned long long* trace;  // optional [grid][16] per-CTA timeline (same slots as igemm_tc2), nullptr = off
@@ -253,6 +254,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                 const __grid_constant__ CUtensorMap tmF_hi, const __grid_constant__ CUtensorMap tmF_lo,
                 const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
+                const __grid_constant__ CUtensorMap tmA6_hi, const __grid_constant__ CUtensorMap tmA6_lo,
                 const IGemm5Params prm) {
   using Cfg = I5Cfg<BN>;
   constexpr int NB = Cfg::NB;
@@ -296,6 +298,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
+    if (prm.halo_split) {
+      tma_prefetch_desc(&tmA6_hi);
+      tma_prefetch_desc(&tmA6_lo);
+    }
     if (prm.tma_out) {
       tma_prefetch_desc(&tmO_hi);
       tma_prefetch_desc(&tmO_lo);
@@ -368,7 +374,17 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (to_mask) mbar_arrive_expect_tx(&f_land[abuf], I5_A_TX);            // own bytes, own barrier
           else if (rank == 0) mbar_arrive_expect_tx(&a_full[abuf], 2 * I5_A_TX);  // bytes of both CTAs
           uint8_t* ah = sA + abuf * I5_A_BUF;
-          if (nxt.kc < prm.kreg) {
+          if (nxt.kc < prm.kreg && prm.halo_split) {
+            // the 18-row halo as three 6-row boxes per plane: a box is fetched as 128-byte rows with a bounded number
+            // of requests in flight, so one 180-row box takes ~8 k cycles from request to complete_tx even out of L2 -
+            // longer than the 6.9 k cycles of MMAs (N = 128) that a double-buffered halo can hide
+#pragma unroll
+            for (int r3 = 0; r3 < 3; ++r3) {
+              i5_tma_load_3d(ah + r3 * 6 * I5_PITCH, &tmA6_hi, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1 + 6 * r3);
+              i5_tma_load_3d(ah + I5_A_PLANE + r3 * 6 * I5_PITCH, &tmA6_lo, &a_full[abuf], nxt.kc * 64, x0 - 1,
+                             y0 - 1 + 6 * r3);
+            }
+          } else if (nxt.kc < prm.kreg) {
             i5_tma_load_3d(ah, &tmA_hi, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
             i5_tma_load_3d(ah + I5_A_PLANE, &tmA_lo, &a_full[abuf], nxt.kc * 64, x0 - 1, y0 - 1);
           } else if (!prm.fmask) {               // fused 1x1 term: same halo geometry on the feature tensor
@@ -458,7 +474,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       uint32_t bfpar = 0, a_word = 0;
       uint32_t par_full = 0, par_masked = 0;   // bit b = parity of the next phase of a_full[b] / a_masked[b]
       int abuf = 0;
-      long long w_full = 0, w_tempty = 0;
+      long long w_full = 0, w_full_a = 0, w_tempty = 0;
       bool first = true;
       while (w < w1) {
         const int ks = w % tpt;
@@ -485,7 +501,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               mbar_wait(&a_full[abuf], (par_full >> abuf) & 1u, 64);
               par_full ^= 1u << abuf;
             }
-            if (tr) w_full += clock64() - tw2;
+            if (tr) w_full_a += clock64() - tw2;
             a_word = a_word0 + (uint32_t)abuf * (uint32_t)(I5_A_BUF >> 4);
           }
           if (kc < prm.kreg || tap == 4) {       // (a fused 1x1 chunk multiplies its centre tap only)
@@ -554,7 +570,8 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       if (tr) {
         tr[T5_CLK_MMA_END] = (unsigned long long)clock64();
-        tr[T5_W_FULL] = (unsigned long long)w_full;
+        // low 32 bits: cycles waiting for B stages, high 32 bits: cycles waiting for halos
+        tr[T5_W_FULL] = ((unsigned long long)w_full_a << 32) | ((unsigned long long)w_full & 0xffffffffull);
         tr[T5_W_TMEM_EMPTY] = (unsigned long long)w_tempty;
       }
     }
@@ -967,7 +984,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   }
   prm.knob = knob;
 
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi, tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo, tmA6_hi, tmA6_lo;
   {
     const uint64_t dims[3] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.H};
     const uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)a.W * a.C * 2};
@@ -976,6 +993,19 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
     if (rc) return rc;
     rc = make_tmap_bf16(&tmA_lo, a.lo, 3, dims, strides, box);
     if (rc) return rc;
+    const uint32_t box6[3] = {64u, (uint32_t)I5_HW, (uint32_t)(I5_HR / 3)};   // a third of it: 6 rows
+    rc = make_tmap_bf16(&tmA6_hi, a.hi, 3, dims, strides, box6);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmA6_lo, a.lo, 3, dims, strides, box6);
+    if (rc) return rc;
+  }
+  {
+    static int halo_split = -1;
+    if (halo_split < 0) {
+      const char* e = getenv("SMB_PH_HALO_SPLIT");
+      halo_split = (e && atoi(e)) ? 1 : 0;
+    }
+    prm.halo_split = halo_split;
   }
   {
     const uint64_t dims[3] = {(uint64_t)b.K, (uint64_t)b.N, (uint64_t)b.taps};
@@ -1049,7 +1079,7 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   const long long pairs = std::max<long long>(1, std::min<long long>(num_sms / 2, prm.total_units / prm.align));
   const int threads = (prm.fmask && prm.kreg < prm.kchunks) ? I5_THREADS_MASK : I5_THREADS;
   SMB_LAUNCH(igemm_ph_kernel<BN>, (unsigned)(2 * pairs), threads, Cfg::SMEM, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, tmO_hi,
-             tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo, prm);
+             tmO_lo, tmF_hi, tmF_lo, tmG_hi, tmG_lo, tmA6_hi, tmA6_lo, prm);
   return SMB_OK;
 }
 

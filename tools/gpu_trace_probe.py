@@ -32,7 +32,8 @@ for r in t.tolist():
                  "cycles": d["clk_out"] - c0, "prologue": d["clk_prologue"] - c0, "mma_first": d["clk_mma_first"] - c0,
                  "tma_end": d["clk_tma_end"] - c0, "mma_end": d["clk_mma_end"] - c0, "epi_first": d["clk_epi_first"] - c0,
                  "epi_end": d["clk_epi_end"] - c0, "w_flags": d["w_flags"], "w_tmem_full": d["w_tmem_full"],
-                 "w_full": d["w_full"], "w_tmem_empty": d["w_tmem_empty"], "w_empty": d["w_empty"]})
+                 "w_full": d["w_full"] & 0xffffffff, "w_full_halo": d["w_full"] >> 32,
+                 "w_tmem_empty": d["w_tmem_empty"], "w_empty": d["w_empty"]})
 import statistics as st
 summ = {k: {"min": min(r[k] for r in rows), "med": st.median(r[k] for r in rows), "max": max(r[k] for r in rows)}
         for k in rows[0] if k != "smid"}
