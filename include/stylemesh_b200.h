@@ -173,6 +173,20 @@ int smb_mip_downsample2x(const float* src_chw, int H, int W, float* dst_chw, voi
 int smb_mip_preview(const float* const* mips, const int* mip_w, const int* mip_h, int num_mips, const float* uv,
                     int uv_channels, int H, int W, float lod_bias, unsigned char* rgb_hwc, void* stream);
 
+/* UV / angle / depth rasteriser: one camera pose of the reference's OpenGL renderer
+ * (scripts/scannet/render_uv: src/renderer/renderer.cpp:165-224, scannet_renderer.cpp:19-62, include/util.h:11-35,
+ * shader/{uvmap,angle,depth}.{vs,frag}) without a GL context.  All pointers are device pointers except view3x4 / proj6.
+ *   verts [nv][3] fp32, faces [nf][3] int32, corner_uv [nf][3][2], corner_normal [nf][3][3] (per face corner);
+ *   view3x4: HOST, the first three rows of the view matrix (row-major); proj6: HOST, (P00, P02, P11, P12, P22, P23) of
+ *   the projection; w x h: output size; tex_size: size of the texture the LOD is queried against (1024 in the reference);
+ *   eye_scratch [nv][4] fp32 and zbuf [h*w] uint64: work buffers;
+ *   uv_out = (u, v, lod), angle_out = cos(view angle) x 3, depth_out = eye depth x 3, each [h][w][3] fp32; pixels
+ *   without geometry are 0; flip != 0 writes GL row j to image row h-1-j (Renderer::saveUV). */
+int smb_raster_view(const float* verts, int num_verts, const int* faces, int num_faces, const float* corner_uv,
+                    const float* corner_normal, const float* view3x4, const float* proj6, int w, int h, float near_plane,
+                    float far_plane, float tex_size, int flip, float* eye_scratch, unsigned long long* zbuf,
+                    float* uv_out, float* angle_out, float* depth_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * VGG / loss engine (replaces model/losses/content_and_style_losses.py: VGG.forward :47-70,
  * GramMatrix :74-80, masked_features :136-143, the loss loop of ContentAndStyleLoss.forward :298-348, and the

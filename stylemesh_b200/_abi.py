@@ -49,6 +49,7 @@ PROTOTYPES = [
     ("smb_texture_post_rgb8", _i, [_p, _i, _i, _p, _p]),
     ("smb_mip_downsample2x", _i, [_p, _i, _i, _p, _p]),
     ("smb_mip_preview", _i, [_pp, _ip, _ip, _i, _p, _i, _i, _i, _f, _p, _p]),
+    ("smb_raster_view", _i, [_p, _i, _p, _i, _p, _p, _p, _p, _i, _i, _f, _f, _f, _i, _p, _p, _p, _p, _p, _p]),
     ("smb_ctx_create", _p, []),
     ("smb_ctx_destroy", None, [_p]),
     ("smb_ctx_set_impl", _i, [_p, _i, _i]),

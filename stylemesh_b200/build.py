@@ -21,7 +21,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libstylemesh_b200.so")
 STAMP_PATH = os.path.join(LIB_DIR, "build.stamp")
 
-SOURCES = ["texture_kernels.cu", "vgg_simt_kernels.cu", "tc_kernels.cu", "tc_igemm_v2.cu", "tc_conv_first.cu", "tc_igemm_v5.cu", "view_prep_kernels.cu", "mask_plan_kernels.cu", "export_kernels.cu", "engine.cu"]
+SOURCES = ["texture_kernels.cu", "vgg_simt_kernels.cu", "tc_kernels.cu", "tc_igemm_v2.cu", "tc_conv_first.cu", "tc_igemm_v5.cu", "view_prep_kernels.cu", "mask_plan_kernels.cu", "export_kernels.cu", "raster_kernels.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

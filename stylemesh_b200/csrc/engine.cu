@@ -541,6 +541,15 @@ int smb_mip_preview(const float* const* mips, const int* mip_w, const int* mip_h
                             (cudaStream_t)stream);
 }
 
+int smb_raster_view(const float* verts, int num_verts, const int* faces, int num_faces, const float* corner_uv,
+                    const float* corner_normal, const float* view3x4, const float* proj6, int w, int h, float near_plane,
+                    float far_plane, float tex_size, int flip, float* eye_scratch, unsigned long long* zbuf,
+                    float* uv_out, float* angle_out, float* depth_out, void* stream) {
+  return launch_raster_view(verts, num_verts, faces, num_faces, corner_uv, corner_normal, view3x4, proj6, w, h,
+                            near_plane, far_plane, tex_size, flip, eye_scratch, zbuf, uv_out, angle_out, depth_out,
+                            (cudaStream_t)stream);
+}
+
 // ---- context --------------------------------------------------------------------------------------------------
 smb_ctx* smb_ctx_create(void) {
   int dev = -1;

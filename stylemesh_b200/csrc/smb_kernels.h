@@ -66,6 +66,10 @@ int launch_texture_post_rgb8(const float* bgr_chw, int H, int W, unsigned char* 
 int launch_mip_downsample2x(const float* src, int Hs, int Ws, float* dst, cudaStream_t st);
 int launch_mip_preview(const float* const* mips, const int* mW, const int* mH, int num_mips, const float* uv,
                        int uv_channels, int H, int W, float lod_bias, unsigned char* rgb_hwc, cudaStream_t st);
+int launch_raster_view(const float* verts, int nv, const int* faces, int nf, const float* corner_uv,
+                       const float* corner_normal, const float* view3x4, const float* proj6, int w, int h, float near,
+                       float far, float tex_size, int flip, float* eye_scratch, unsigned long long* zbuf, float* uv_out,
+                       float* angle_out, float* depth_out, cudaStream_t st);
 #define SMB_MAX_PLAN_LAYERS 8
 int launch_view_level_masks(const unsigned char* mask, const long long* rounded, const long long* other,
                             const float* interp_w, int H, int W, int L, float* level_mask, float* level_weight,
