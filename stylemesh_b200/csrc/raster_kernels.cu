@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const float4* __res
       const float nn = rsqrtf(fmaxf(val[2] * val[2] + val[3] * val[3] + val[4] * val[4], 1e-30f));
       const float pn = rsqrtf(fmaxf(val[5] * val[5] + val[6] * val[6] + val[7] * val[7], 1e-30f));
       r_ang = fmaxf(-(val[2] * val[5] + val[3] * val[6] + val[4] * val[7]) * nn * pn, 0.f);
-      const float z_ndc = __uint_as_float((unsigned)(key >> 32)) * 2.f - 1.f;
-      r_dep = (2.f * cam.near * cam.far) / (cam.far + cam.near - z_ndc * (cam.far - cam.near));
+      // LinearizeDepth(gl_FragCoord.z) of depth.frag is the eye depth = 1 / (interpolated 1 / w_clip); taken from the
+      // perspective interpolation rather than by inverting the float32 window depth (whose error grows with depth^2)
+      r_dep = 1.f / denom;
     }
     uv_out[o] = r_uv[0]; uv_out[o + 1] = r_uv[1]; uv_out[o + 2] = r_uv[2];
     ang_out[o] = ang_out[o + 1] = ang_out[o + 2] = r_ang;
