@@ -257,3 +257,52 @@ def test_checkpoint_round_trip_restores_texels_moments_step_and_lr(monkeypatch, 
         o.step()
     for ma, mb in zip(a.texture.layers, b.texture.layers):
         assert torch.equal(ma.data, mb.data)
+
+
+def test_fused_pipeline_average_gram_mode_with_a_multi_level_pyramid(monkeypatch, tmp_path):
+    """gram_mode='average' (cs:319-323) on a 3-level pyramid with the angle split ('multi'): the Gram cache is shared by
+    the levels of a step and carried across steps; the fused training path must follow the oracle over several steps
+    (losses and dense gradients, teacher-forced on identical texels)."""
+    fake_engine.install(monkeypatch)
+    from stylemesh_b200.model.model import TextureOptimizationStyleTransferPipeline
+    from oracle import stylemesh_oracle as orc
+    spec = golden_case_specs()["with_angle_and_depth"]
+    preset, sd, layers, view, style, hierarchical = build_inputs(spec)
+    vgg_path = os.path.join(tmp_path, "vgg.pth")
+    torch.save(sd, vgg_path)
+    W, H = spec["tex_size"]
+    mdl = TextureOptimizationStyleTransferPipeline(
+        W, H, hierarchical_texture=True, hierarchical_layers=len(layers), random_texture_init=True,
+        style_image=style.clone(), style_weights=list(preset["style_weights"]), vgg_gatys_model_path=vgg_path,
+        use_angle_weight=True, use_depth_scaling=True, style_pyramid_mode="multi", gram_mode="average",
+        angle_threshold=preset["angle_threshold"], learning_rate=1.0, loss_weights=dict(preset["loss_weights"]),
+        save_texture=False)
+    with torch.no_grad():
+        for m, t in zip(mdl.texture.layers, layers):
+            m.data.copy_(t)
+    loss = orc.StyleContentOracle(vgg_params=sd, style_weights=list(preset["style_weights"]),
+                                  angle_threshold=preset["angle_threshold"], style_pyramid_mode="multi",
+                                  gram_mode="average", as_written=False)
+    loss.set_style_image(style.unsqueeze(0))
+    cfg = orc.OracleConfig(use_angle_weight=True, use_depth_scaling=True, loss_weights=dict(preset["loss_weights"]),
+                           hierarchical=True, learning_rate=1.0)
+    pipe = orc.OraclePipeline(layers, loss, cfg)
+    (opt,), _ = mdl.configure_optimizers()
+    batch = view.as_batch()
+    lam = float(mdl.loss_weights["tex_reg"])
+    for step in range(3):
+        with torch.no_grad():
+            for t, m in zip(pipe.layers, mdl.texture.layers):
+                t.copy_(m.data)
+        want, want_grads = pipe.grads(batch)
+        out = mdl.training_step(batch, step)
+        buf = mdl._loss_buf
+        for k, i in (("style", 0), ("content", 1), ("tex_reg", 2), ("total", 3)):
+            assert rel(float(buf[i]), want[k]) < 1e-4, (step, k, float(buf[i]), want[k])
+        for l, (g, gg) in enumerate(zip(mdl._grad_tensors(), want_grads)):
+            x = pipe.layers[l].detach().clamp(orc.CLAMP_LO, orc.CLAMP_HI)
+            data_want = gg - lam * mdl.tex_reg_weights[l] * 2.0 * x / x.numel()
+            assert (g - data_want).norm() <= 1e-4 * data_want.norm() + 1e-12, (step, l)
+        out["loss"].backward()
+        opt.step()
+    assert all(len(v) == 9 for v in mdl.vgg_loss.gram_cache.values())        # 3 levels x 3 steps, capped at 10
