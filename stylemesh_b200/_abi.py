@@ -11,6 +11,8 @@ import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libstylemesh_b200.so")
+if os.environ.get("SMB_LIB"):            # kernel experiments: an alternative build of the same ABI (tools/build_variant.sh)
+    LIB_PATH = os.environ["SMB_LIB"]
 
 NUM_VGG_CONVS = 13
 IMPL_SIMT = 0

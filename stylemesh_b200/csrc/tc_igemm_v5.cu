@@ -55,7 +55,10 @@ struct I5Cfg {
   // layers are not bound by shared-memory reads alone.  The default keeps main + corr = 128 columns and uses the
   // freed TMEM for FOUR tile buffers: with 9 taps of N = 64 per tile (1.8 us of MMAs) the commit -> epilogue ->
   // remote-arrive round trip of a buffer is longer than the MMAs of the one other tile a double buffer can hide.)
-  static constexpr bool WIDE64 = false;
+#ifndef SMB_PH_WIDE64
+#define SMB_PH_WIDE64 0
+#endif
+  static constexpr bool WIDE64 = SMB_PH_WIDE64 != 0;
   static constexpr int TBUF = (BN == 64 && WIDE64) ? 192 : 2 * BN;
   static constexpr int NT = (BN == 64 && !WIDE64) ? 4 : 2;              // tile buffers in TMEM
   static constexpr int TMEM_NEED = NT * TBUF;
