@@ -81,7 +81,7 @@ struct IGemm5Params {
   unsigned int epoch;
   int resident;               // 1: one K-chunk, one N tile -> the 9 B tiles are loaded once and stay in stages 0..8
   int knob;                   // experiment bits (SMB_PH_KNOB): 32 = no weight prefetch before griddepcontrol.wait,
-                              // 1 = request the next halo as early as possible,
+                              // 1 = block for the next halo at tap 3 (round-1 behaviour) instead of trying at every tap,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
   int halo_split;             // 1: the activation halo is requested as three 6-row boxes per plane (SMB_PH_HALO_SPLIT)
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do,
@@ -460,7 +460,10 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       for (int w = prm.resident ? w1 : w0; w < w1; ++w) {
         if (a_next == u + 1 && a_next <= a_last) {
-          if (prm.knob & 1) issue_A(tap == 8);
+          // the next halo is requested as soon as its buffer is free (tried at every tap, forced at the last one); the
+          // round-1 default - block for it at tap 3 - also held back the B tiles of taps 3..8 (knob 1 restores it;
+          // measured on one box: 427.9 -> 431.4 views/s, profiles/r02l_bench_{base,knob1}.json)
+          if (!(prm.knob & 1)) issue_A(tap == 8);
           else if (tap >= 3) issue_A(true);
         }
         const bool fused = cur.kc >= prm.kreg;
