@@ -58,7 +58,7 @@ struct I5Cfg {
 #ifndef SMB_PH_WIDE64
 #define SMB_PH_WIDE64 0
 #endif
-  static constexpr bool WIDE64 = SMB_PH_WIDE64 != 0;
+  static constexpr bool WIDE64 = SMB_PH_WIDE64 != 0;   // compile flag, see DESIGN §4
   static constexpr int TBUF = (BN == 64 && WIDE64) ? 192 : 2 * BN;
   static constexpr int NT = (BN == 64 && !WIDE64) ? 4 : 2;              // tile buffers in TMEM
   static constexpr int TMEM_NEED = NT * TBUF;
@@ -80,8 +80,7 @@ struct IGemm5Params {
   unsigned int* flags;        // [grid]
   unsigned int epoch;
   int resident;               // 1: one K-chunk, one N tile -> the 9 B tiles are loaded once and stay in stages 0..8
-  int knob;                   // experiment bits (SMB_PH_KNOB): 32 = no weight prefetch before griddepcontrol.wait,
-                              // 1 = block for the next halo at tap 3 (round-1 behaviour) instead of trying at every tap,
+  int knob;                   // experiment bits (SMB_PH_KNOB): 1 = request the next halo as early as possible,
                               // 2 = epilogue drains TMEM but computes / stores nothing, 4 = no MMAs, 8 = no TMA loads
   int halo_split;             // 1: the activation halo is requested as three 6-row boxes per plane (SMB_PH_HALO_SPLIT)
   int tma_out;                // 1: hi/lo planes leave through shared memory + TMA tensor stores, 2: fp32 rows do,
@@ -341,19 +340,15 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   i5_cluster_sync();                         // peer barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // griddepcontrol.wait (pdl_sync) is executed per role below: everything above overlaps the tail of the preceding
-  // launch, and the producer thread additionally requests its first WEIGHT tiles before it waits (weights are written
-  // once at load time, never by a preceding launch)
-  const bool is_producer_thread = (warp == 0) && elect_one();
-  if (!is_producer_thread) pdl_sync();
-  if (tr && threadIdx.x == 32) tr[T5_CLK_PROLOGUE] = (unsigned long long)clock64();
+  pdl_sync();                                // everything above overlaps the tail of the preceding launch
+  if (tr && threadIdx.x == 0) tr[T5_CLK_PROLOGUE] = (unsigned long long)clock64();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own halo, own half of B) =====================
     // Program order: halo of the first unit; then one B tile per work unit (tap), with the NEXT unit's halo issued
     // at tap 3 of the current one (it only needs the other A buffer to be drained).  A range may start / end in the
     // middle of a halo unit.  All indices are walked incrementally: this single thread has ~768 cycles per tap.
-    if (is_producer_thread) {
+    if (elect_one()) {
       const int w0 = (int)u0, w1 = (int)u1;
       UnitWalk cur, nxt;
       cur.init(w0 / 9, ipt, prm.tiles_n);
@@ -363,40 +358,6 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       int ga = 0, bs = 0;
       uint32_t bpar = 1;                       // parity of a never-completed phase: the first NB waits pass at once
       long long w_empty = 0;
-      // ---- before griddepcontrol.wait: the B tiles of the first work units (all nine when they stay resident) ----
-      int b_pre = 0;                           // B tiles already requested here; the main loop skips that many
-      const bool pre_on = !(prm.knob & 32) && !(prm.knob & 8);
-      if (pre_on && prm.resident) {
-        for (int t9 = 0; t9 < 9; ++t9) {
-          if (rank == 0) mbar_arrive_expect_tx(&b_full[t9], 2 * Cfg::B_STAGE);
-          uint8_t* bh = sB + t9 * Cfg::B_STAGE;
-          const int nb0 = (int)rank * (BN / 2);
-          i5_tma_load_3d(bh, &tmB_hi, &b_full[t9], 0, nb0, t9);
-          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[t9], 0, nb0, t9);
-        }
-        b_pre = 9;
-      } else if (pre_on) {
-        UnitWalk pw = cur;
-        int ptap = tap;
-        for (int w = w0; w < w1 && b_pre < NB && pw.kc < prm.kreg; ++w) {      // stops at the first fused (Gram) chunk
-          if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * Cfg::B_STAGE);
-          uint8_t* bh = sB + bs * Cfg::B_STAGE;
-          const int nb0 = pw.n_tile * BN + (int)rank * (BN / 2);
-          i5_tma_load_3d(bh, &tmB_hi, &b_full[bs], pw.kc * 64, nb0, ptap);
-          i5_tma_load_3d(bh + Cfg::B_PLANE, &tmB_lo, &b_full[bs], pw.kc * 64, nb0, ptap);
-          ++b_pre;
-          if (++bs == NB) {
-            bs = 0;
-            bpar ^= 1u;
-          }
-          if (++ptap == 9) {
-            ptap = 0;
-            pw.next(ipt, prm.tiles_n);
-          }
-        }
-      }
-      pdl_sync();
-      if (tr) tr[T5_W_EMPTY] = ((unsigned long long)clock64() & 0xffffffffull) << 32;   // high half: low clock bits when the producer passed the dependency wait
       // request the halo of unit `nxt` into the next A buffer; `force` = wait for the buffer, else give up if the
       // MMAs of the unit that used it two units ago have not completed yet (the caller retries at the next tap)
       auto issue_A = [&](bool force) -> bool {
@@ -445,7 +406,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (prm.resident) {
         // every tile of this layer multiplies the same nine B tiles (all CTAs would otherwise stream the same 144 KB
         // from a handful of L2 lines): load them once, then only halos move
-        for (int t9 = b_pre; t9 < 9; ++t9) {
+        for (int t9 = 0; t9 < 9; ++t9) {
           if (prm.knob & 8) {
             if (rank == 0) mbar_arrive(&b_full[t9]);
             continue;
@@ -460,16 +421,11 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       for (int w = prm.resident ? w1 : w0; w < w1; ++w) {
         if (a_next == u + 1 && a_next <= a_last) {
-          // the next halo is requested as soon as its buffer is free (tried at every tap, forced at the last one); the
-          // round-1 default - block for it at tap 3 - also held back the B tiles of taps 3..8 (knob 1 restores it;
-          // measured on one box: 427.9 -> 431.4 views/s, profiles/r02l_bench_{base,knob1}.json)
-          if (!(prm.knob & 1)) issue_A(tap == 8);
+          if (prm.knob & 1) issue_A(tap == 8);
           else if (tap >= 3) issue_A(true);
         }
         const bool fused = cur.kc >= prm.kreg;
-        if ((!fused || tap == 4) && b_pre > 0) {
-          --b_pre;                               // requested before the dependency wait
-        } else if (!fused || tap == 4) {         // a fused chunk has one B tile (centre tap), the other taps are no-ops
+        if (!fused || tap == 4) {                // a fused chunk has one B tile (centre tap), the other taps are no-ops
           const long long tw0 = tr ? clock64() : 0;
           mbar_wait(&b_empty[bs], bpar, 62);
           if (tr) w_empty += clock64() - tw0;
@@ -500,7 +456,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       if (tr) {
         tr[T5_CLK_TMA_END] = (unsigned long long)clock64();
-        tr[T5_W_EMPTY] = (tr[T5_W_EMPTY] & 0xffffffff00000000ull) | ((unsigned long long)w_empty & 0xffffffffull);
+        tr[T5_W_EMPTY] = (unsigned long long)w_empty;
       }
     }
   } else if (warp == 1) {
@@ -521,7 +477,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       uint32_t bfpar = 0, a_word = 0;
       uint32_t par_full = 0, par_masked = 0;   // bit b = parity of the next phase of a_full[b] / a_masked[b]
       int abuf = 0;
-      long long w_full = 0, w_full_a = 0, w_tempty = 0, first_a = 0;
+      long long w_full = 0, w_full_a = 0, w_tempty = 0;
       bool first = true;
       while (w < w1) {
         const int ks = w % tpt;
@@ -548,11 +504,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               mbar_wait(&a_full[abuf], (par_full >> abuf) & 1u, 64);
               par_full ^= 1u << abuf;
             }
-            if (tr) {
-              const long long now = clock64();
-              w_full_a += now - tw2;
-              if (first) first_a = now;
-            }
+            if (tr) w_full_a += clock64() - tw2;
             a_word = a_word0 + (uint32_t)abuf * (uint32_t)(I5_A_BUF >> 4);
           }
           if (kc < prm.kreg || tap == 4) {       // (a fused 1x1 chunk multiplies its centre tap only)
@@ -623,8 +575,7 @@ igemm_ph_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tr[T5_CLK_MMA_END] = (unsigned long long)clock64();
         // low 32 bits: cycles waiting for B stages, high 32 bits: cycles waiting for halos
         tr[T5_W_FULL] = ((unsigned long long)w_full_a << 32) | ((unsigned long long)w_full & 0xffffffffull);
-        // high half: low clock bits when the first halo was complete in both CTAs
-        tr[T5_W_TMEM_EMPTY] = (((unsigned long long)first_a & 0xffffffffull) << 32) | ((unsigned long long)w_tempty & 0xffffffffull);
+        tr[T5_W_TMEM_EMPTY] = (unsigned long long)w_tempty;
       }
     }
   } else if (warp < 10) {

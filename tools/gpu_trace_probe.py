@@ -33,10 +33,7 @@ for r in t.tolist():
                  "tma_end": d["clk_tma_end"] - c0, "mma_end": d["clk_mma_end"] - c0, "epi_first": d["clk_epi_first"] - c0,
                  "epi_end": d["clk_epi_end"] - c0, "w_flags": d["w_flags"], "w_tmem_full": d["w_tmem_full"],
                  "w_full": d["w_full"] & 0xffffffff, "w_full_halo": (d["w_full"] >> 32) & 0xffffffff,
-                 "w_tmem_empty": d["w_tmem_empty"] & 0xffffffff, "w_empty": d["w_empty"] & 0xffffffff,
-                 # low-32-bit clock stamps relative to the CTA's start (0 where the role does not run in this CTA)
-                 "first_halo": (((d["w_tmem_empty"] >> 32) - c0) & 0xffffffff) if (d["w_tmem_empty"] >> 32) else 0,
-                 "dep_wait_done": (((d["w_empty"] >> 32) - c0) & 0xffffffff) if (d["w_empty"] >> 32) else 0})
+                 "w_tmem_empty": d["w_tmem_empty"], "w_empty": d["w_empty"]})
 import statistics as st
 summ = {k: {"min": min(r[k] for r in rows), "med": st.median(r[k] for r in rows), "max": max(r[k] for r in rows)}
         for k in rows[0] if k != "smid"}
