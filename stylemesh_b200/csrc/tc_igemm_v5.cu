@@ -983,7 +983,9 @@ static int launch_igemm_ph_bn(const Act& a, const PackedB& b, const Epilogue& ep
   static int knob = -1;
   if (knob < 0) {
     const char* e = getenv("SMB_PH_KNOB");
-    knob = e ? atoi(e) : 0;
+    knob = e ? atoi(e) : 1;      // default: bit 0 set - the next halo is requested as soon as its buffer is free (tried at
+                                 // every tap, forced at the last) instead of blocking for it at tap 3, which also held
+                                 // back the B tiles of taps 3..8: +0.6 % on the step (profiles/r02o_bench_{product,knob1}.json)
   }
   prm.knob = knob;
 
