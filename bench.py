@@ -182,7 +182,8 @@ def one_step(mdl, opt, batch, i):
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, mean per launch, from the committed
-    `ncu --set full` summary (profiles/, written by tools/ncu_summary.py); (None, None) when there is none."""
+    ncu summary (profiles/, written by tools/ncu_summary.py from a `--set full` report or by
+    tools/ncu_metrics_report.py from a metrics pass); (None, None) when there is none."""
     import glob
     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
@@ -191,7 +192,8 @@ def ncu_traffic_per_launch():
         return float(val.replace(",", "")) * units[unit]
 
     paths = glob.glob(os.path.join(REPO, "profiles", "*ncu_full*ph*.json")) + \
-        glob.glob(os.path.join(REPO, "profiles", "*ncu_full_step*.json"))
+        glob.glob(os.path.join(REPO, "profiles", "*ncu_full_step*.json")) + \
+        glob.glob(os.path.join(REPO, "profiles", "*ncu_metrics_step*.json"))     # same counters, metrics-only pass
     for path in sorted(paths, key=os.path.basename, reverse=True):       # newest round tag first
         try:
             rows = [r for r in json.load(open(path)) if "igemm_ph_kernel" in r.get("Kernel Name", "")]
