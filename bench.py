@@ -471,13 +471,17 @@ def run_ours(args):
                         "ms_per_launch": opt_ms,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)" if peaks else "fallback 6.4 TB/s"}
         else:
-            wire = 4.0 * numel * (world - 1) / world          # bytes a rank pulls (gradient slices) = bytes it pushes (texels)
+            # per rank and direction: the gradient slices it pulls from N-1 peers come IN, the same amount of its own
+            # gradient goes OUT to the peers' pulls; the texel slice it pushes to N-1 peers goes OUT, the peers' pushes
+            # come IN -> 2 (N-1)/N of the flat buffer each way
+            wire = 2.0 * 4.0 * numel * (world - 1) / world
             roof_hbm = {"kernel": "dist_adam_kernel + dist_adam_finish_kernel", "ms_per_step": opt_ms,
                         "bound": "nvlink", "wire_bytes_per_direction_per_rank": wire,
                         "nvlink_gbs_per_direction": wire / (opt_ms * 1e-3) / 1e9, "nvlink_peak_gbs_per_direction": 900.0,
                         "note": "reduce-scatter + Adam on the rank's slice + all-gather over NVLink, gradient reset; "
-                                "the time includes waiting for the slowest rank's backward, so the GB/s is a lower "
-                                "bound on what the kernel moves while it runs; 900 GB/s is the nominal NVLink 5 figure"}
+                                "the time includes waiting for the slowest rank's backward and the Adam arithmetic, so the "
+                                "GB/s is a lower bound on what the links carry while the kernel runs; 900 GB/s is the "
+                                "nominal NVLink 5 figure per direction"}
 
     # ------------------------------------------------ CPU baseline (oracle port) -------------------------------
     cpu = None
